@@ -1,0 +1,208 @@
+// Binning: depth order of the Gaussians, offsets scan, (tile, Gaussian) instance emission, tile
+// sort and per-tile ranges.  Contract: the sorted Gaussian-id list and the tile ranges equal the
+// reference's point_list / ranges bit for bit (rasterizer_impl.cu:70-138, :277-321).
+//
+// The reference sorts R instances by a 64-bit key [tile | depth bits] with one stable radix sort
+// (~6 passes over 12 B/instance, R ~ 25-30 x P).  The same total order — tile, then depth bits,
+// then ascending Gaussian id for ties (stability) — is produced here by
+//   1. a stable sort of the P Gaussians by depth bits (32-bit keys, P items; input order is the
+//      id order, so ties keep ascending id),
+//   2. emitting instances in that order with a 32-bit tile key,
+//   3. a stable radix sort of the R instances by the tile bits only (ceil(log2(#tiles)) bits,
+//      2 passes for 8160 tiles) carrying the 32-bit Gaussian id.
+// A stable sort by tile of a depth-ordered sequence is depth-ordered inside every tile, so the
+// result is identical while the R-sized traffic drops from ~6x(12+12) B to 2x(8+8) B per instance.
+#include <cub/cub.cuh>
+#include "common.cuh"
+
+namespace sgb {
+
+namespace {
+
+// tiles_touched in depth order, as an input iterator for the scan (no materialised gather).
+struct PermutedCount {
+    const uint32_t* perm;
+    const uint32_t* tiles_touched;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& i) const {
+        return tiles_touched[perm[i]];
+    }
+};
+
+__global__ void iota_kernel(int P, uint32_t* v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) v[i] = i;
+}
+
+// One warp handles 32 consecutive slots of the depth order; for each visible Gaussian its lanes
+// write the tile keys / ids of its rectangle cooperatively (coalesced), instead of one thread
+// walking the whole rectangle (duplicateWithKeys, rasterizer_impl.cu:70-111).
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ perm,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const SplatRec* __restrict__ rec,
+                                                             const int* __restrict__ radii, dim3 grid,
+                                                             uint32_t* __restrict__ keys,
+                                                             uint32_t* __restrict__ vals) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    uint32_t gid = 0, off = 0, n = 0, x0 = 0, y0 = 0, w = 0;
+    if (slot < P) {
+        gid = perm[slot];
+        int r = radii[gid];
+        if (r > 0) {
+            off = (slot == 0) ? 0 : offsets[slot - 1];
+            float4 a = __ldg(reinterpret_cast<const float4*>(rec + gid));
+            uint2 rmin, rmax;
+            get_rect(make_float2(a.x, a.y), r, rmin, rmax, grid);
+            x0 = rmin.x; y0 = rmin.y;
+            w = rmax.x - rmin.x;
+            n = w * (rmax.y - rmin.y);
+        }
+    }
+    unsigned any = __ballot_sync(0xffffffffu, n > 0);
+    while (any) {
+        int src = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t g = __shfl_sync(0xffffffffu, gid, src);
+        uint32_t o = __shfl_sync(0xffffffffu, off, src);
+        uint32_t nn = __shfl_sync(0xffffffffu, n, src);
+        uint32_t xx = __shfl_sync(0xffffffffu, x0, src);
+        uint32_t yy = __shfl_sync(0xffffffffu, y0, src);
+        uint32_t ww = __shfl_sync(0xffffffffu, w, src);
+        for (uint32_t k = lane; k < nn; k += 32) {
+            uint32_t ty = k / ww, tx = k - ty * ww;
+            keys[o + k] = (yy + ty) * grid.x + (xx + tx);  // key = y*grid.x + x, rasterizer_impl.cu:102
+            vals[o + k] = g;
+        }
+    }
+}
+
+// rasterizer_impl.cu:116-138 on 32-bit tile keys.
+__global__ void identify_ranges_kernel(int64_t L, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    uint32_t cur = keys[idx];
+    if (idx == 0)
+        ranges[cur].x = 0;
+    else {
+        uint32_t prev = keys[idx - 1];
+        if (cur != prev) {
+            ranges[prev].y = (uint32_t)idx;
+            ranges[cur].x = (uint32_t)idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+// rasterizer_impl.cu:35-50
+uint32_t higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step;
+        else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+}  // namespace
+
+int Scratch::ensure(size_t n) {
+    if (n <= cap) return SGB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 3) + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        p = nullptr;
+        return SGB_E_NOMEM;
+    }
+    cap = want;
+    return SGB_OK;
+}
+
+// preprocess -> depth order -> scan -> R (one stream sync, like rasterizer_impl.cu:283).
+int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g, int32_t* radii,
+                             int64_t* R_host, cudaStream_t s) {
+    const int P = in.P;
+    // scratch layout: keys_in | keys_out | vals_in | vals_out(perm) | offsets | cub temp
+    size_t sort_tmp = 0, scan_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, P, 0, 32, s);
+    {
+        cub::CountingInputIterator<uint32_t> cnt(0);
+        PermutedCount op{nullptr, nullptr};
+        cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> it(cnt, op);
+        cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, it, (uint32_t*)nullptr, P, s);
+    }
+    size_t arr = align_up(sizeof(uint32_t) * (size_t)P);
+    size_t tmp = align_up(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
+    int rc = ctx->geom.ensure(5 * arr + tmp);
+    if (rc) return rc;
+    char* base = (char*)ctx->geom.p;
+    uint32_t* keys_in = (uint32_t*)(base);
+    uint32_t* keys_out = (uint32_t*)(base + arr);
+    uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
+    uint32_t* perm = (uint32_t*)(base + 3 * arr);
+    uint32_t* offsets = (uint32_t*)(base + 4 * arr);
+    void* cub_tmp = base + 5 * arr;
+
+    rc = launch_preprocess(in, g, radii, keys_in, s);
+    if (rc) return rc;
+    iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vals_in);
+    SGB_LAUNCH_CHECK("iota_kernel", in.debug, s);
+    SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_in, keys_out, vals_in, perm, P, 0, 32, s));
+    {
+        cub::CountingInputIterator<uint32_t> cnt(0);
+        PermutedCount op{perm, g.tiles_touched};
+        cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> it(cnt, op);
+        SGB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_tmp, it, offsets, P, s));
+    }
+    uint32_t* h = (uint32_t*)ctx->pinned;
+    SGB_CUDA(cudaMemcpyAsync(h, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SGB_CUDA(cudaStreamSynchronize(s));
+    *R_host = (int64_t)h[0];
+    ctx->last_P = P;
+    ctx->d_perm = perm;
+    ctx->d_offsets = offsets;
+    return SGB_OK;
+}
+
+int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                const int32_t* radii, cudaStream_t s) {
+    dim3 tile_grid((in.W + SGB_TILE - 1) / SGB_TILE, (in.H + SGB_TILE - 1) / SGB_TILE, 1);
+    const size_t tiles = (size_t)tile_grid.x * tile_grid.y;
+    SGB_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), s));  // rasterizer_impl.cu:313
+    if (R == 0) return SGB_OK;
+    if (ctx->last_P != in.P || !ctx->d_perm) {
+        set_error("sgb_forward_render called without a matching sgb_forward_geometry on this ctx");
+        return SGB_E_INVALID;
+    }
+    size_t sort_tmp = 0;
+    const int bits = (int)higher_msb((uint32_t)tiles);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, R, 0, bits, s);
+    size_t arr = align_up(sizeof(uint32_t) * (size_t)R);
+    int rc = ctx->bin.ensure(3 * arr + align_up(sort_tmp));
+    if (rc) return rc;
+    char* base = (char*)ctx->bin.p;
+    uint32_t* keys_unsorted = (uint32_t*)base;
+    uint32_t* keys_sorted = (uint32_t*)(base + arr);
+    uint32_t* vals_unsorted = (uint32_t*)(base + 2 * arr);
+    void* cub_tmp = base + 3 * arr;
+
+    emit_instances_kernel<<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
+                                                            tile_grid, keys_unsorted, vals_unsorted);
+    SGB_LAUNCH_CHECK("emit_instances_kernel", in.debug, s);
+    SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_unsorted, keys_sorted, vals_unsorted,
+                                             b.point_list, R, 0, bits, s));
+    identify_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, im.ranges);
+    SGB_LAUNCH_CHECK("identify_ranges_kernel", in.debug, s);
+    return SGB_OK;
+}
+
+}  // namespace sgb

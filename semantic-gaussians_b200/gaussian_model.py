@@ -1,0 +1,104 @@
+"""The slice of the reference's GaussianModel that the render / fusion path reads
+(model/gaussian_model.py:33-48 activations, :105-144 getters, :188-194 create_semantic).
+Training-state bookkeeping (densify / prune / optimiser / PLY IO) is out of scope."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def build_rotation(r: torch.Tensor) -> torch.Tensor:
+    """utils/general_utils.py:82-104 (normalises the quaternion first)."""
+    q = r / torch.sqrt((r * r).sum(dim=1))[:, None]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device, dtype=r.dtype)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - w * z)
+    R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y)
+    R[:, 2, 1] = 2 * (y * z + w * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def build_scaling_rotation(s: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    """utils/general_utils.py:106-115: L = R @ diag(s)."""
+    L = torch.zeros((s.shape[0], 3, 3), dtype=s.dtype, device=s.device)
+    L[:, 0, 0], L[:, 1, 1], L[:, 2, 2] = s[:, 0], s[:, 1], s[:, 2]
+    return build_rotation(r) @ L
+
+
+def strip_symmetric(sym: torch.Tensor) -> torch.Tensor:
+    """utils/general_utils.py:66-79: upper triangle (xx, xy, xz, yy, yz, zz)."""
+    return torch.stack([sym[:, 0, 0], sym[:, 0, 1], sym[:, 0, 2], sym[:, 1, 1], sym[:, 1, 2], sym[:, 2, 2]], dim=1)
+
+
+class GaussianModel:
+    """Parameter container with the reference's raw-parameter conventions: log scales, logit
+    opacities, unnormalised quaternions, SH as (P,1,3) dc + (P,15,3) rest."""
+
+    def __init__(self, sh_degree: int = 3):
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = sh_degree
+        self._xyz = torch.empty(0)
+        self._features_dc = torch.empty(0)
+        self._features_rest = torch.empty(0)
+        self._scaling = torch.empty(0)
+        self._rotation = torch.empty(0)
+        self._opacity = torch.empty(0)
+        self._features_semantic = torch.empty(0)
+        self._times = torch.empty(0)
+
+    @classmethod
+    def from_activated(cls, xyz, scales, rotations, opacity, shs=None, sh_degree: int = 3, device="cuda"):
+        """Build from activated values (numpy or torch): scales > 0, opacity in (0,1), unit quats."""
+        t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device).contiguous()
+        m = cls(sh_degree)
+        m._xyz = t(xyz)
+        m._scaling = torch.log(t(scales))
+        m._rotation = t(rotations)
+        op = t(opacity).reshape(-1, 1)
+        m._opacity = torch.log(op / (1 - op))
+        if shs is not None:
+            shs = t(shs)
+            m._features_dc = shs[:, :1, :].contiguous()
+            m._features_rest = shs[:, 1:, :].contiguous()
+        return m
+
+    # --- model/gaussian_model.py:105-144
+    @property
+    def get_scaling(self):
+        return torch.exp(self._scaling)
+
+    @property
+    def get_rotation(self):
+        return F.normalize(self._rotation)
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self._opacity)
+
+    def get_covariance(self, scaling_modifier=1):
+        L = build_scaling_rotation(scaling_modifier * self.get_scaling, self._rotation)
+        return strip_symmetric(L @ L.transpose(1, 2))
+
+    def get_covariance_rotation(self, scaling_modifier=1, world_rotate=None):
+        L = build_scaling_rotation(scaling_modifier * self.get_scaling, self._rotation)
+        return strip_symmetric(world_rotate.transpose(0, 1) @ L @ L.transpose(1, 2) @ world_rotate)
+
+    def create_semantic(self, dim: int):
+        """model/gaussian_model.py:188-194: zero per-Gaussian feature sums and view counts."""
+        P, dev = self._xyz.shape[0], self._xyz.device
+        self._features_semantic = torch.zeros((P, dim), dtype=torch.float32, device=dev)
+        self._times = torch.zeros((P, 1), dtype=torch.float32, device=dev)

@@ -1,0 +1,345 @@
+"""Autograd boundary of the rasterizer: the Python surface of the reference's two extensions
+(``channel_rasterization/__init__.py`` and ``rgbd_rasterization/__init__.py``) over libsgb200.
+
+``_C_chn`` / ``_C_rgbd`` reproduce the pybind entry points ``rasterize_gaussians``,
+``rasterize_gaussians_backward`` and ``mark_visible`` (ext.cpp:16-18) with the reference's
+positional argument lists and return tuples; ``make_module`` builds the
+GaussianRasterizationSettings / GaussianRasterizer / _RasterizeGaussians trio for each variant.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], device, what: str) -> Optional[torch.Tensor]:
+    """The reference encodes an absent optional input as an empty tensor → nullptr
+    (channel_rasterization/__init__.py:266-276, rasterize_points.cu:99-117)."""
+    if t is None or t.numel() == 0:
+        return None
+    return _f32(t, device, what)
+
+
+def _f32(t: torch.Tensor, device, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if t.device != device:
+        raise ValueError(f"{what} is on {t.device}, expected {device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream_ctx(device):
+    s = torch.cuda.current_stream(device).cuda_stream
+    return s, _lib.ctx_for(device.index if device.index is not None else torch.cuda.current_device(), s)
+
+
+def _make_inputs(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                 viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered,
+                 debug, num_channels):
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:61-64
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor: the rasterizer has no CPU path")
+    dev = means3D.device
+    keep = dict(
+        background=_f32(background, dev, "bg"), means3D=_f32(means3D, dev, "means3D"),
+        colors=_opt(colors, dev, "colors_precomp"), opacity=_f32(opacity, dev, "opacities"),
+        scales=_opt(scales, dev, "scales"), rotations=_opt(rotations, dev, "rotations"),
+        cov3D=_opt(cov3D_precomp, dev, "cov3D_precomp"), view=_f32(viewmatrix, dev, "viewmatrix"),
+        proj=_f32(projmatrix, dev, "projmatrix"), sh=_opt(sh, dev, "shs"), campos=_f32(campos, dev, "campos"))
+    P = means3D.size(0)
+    M = keep["sh"].size(1) if keep["sh"] is not None else 0  # rasterize_points.cu:88-92
+    if keep["background"].numel() < num_channels:
+        raise RuntimeError(f"bg has {keep['background'].numel()} entries, need {num_channels}")
+    if keep["colors"] is not None and keep["colors"].shape != (P, num_channels):
+        raise RuntimeError(f"colors_precomp must be ({P}, {num_channels}), got {tuple(keep['colors'].shape)}")
+    inp = _lib.ViewInputs(
+        P=P, D=int(degree), M=int(M), W=int(W), H=int(H), C=int(num_channels),
+        background=_ptr(keep["background"]), means3D=_ptr(keep["means3D"]), shs=_ptr(keep["sh"]),
+        colors_precomp=_ptr(keep["colors"]), opacities=_ptr(keep["opacity"]), scales=_ptr(keep["scales"]),
+        scale_modifier=float(scale_modifier), rotations=_ptr(keep["rotations"]),
+        cov3D_precomp=_ptr(keep["cov3D"]), viewmatrix=_ptr(keep["view"]), projmatrix=_ptr(keep["proj"]),
+        campos=_ptr(keep["campos"]), tan_fovx=float(tan_fovx), tan_fovy=float(tan_fovy),
+        prefiltered=int(bool(prefiltered)), debug=int(bool(debug)))
+    return inp, keep, dev
+
+
+def _forward_impl(want_depth: bool, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                  degree, campos, prefiltered, debug, num_channels):
+    lib = _lib.load()
+    inp, keep, dev = _make_inputs(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                                  image_width, sh, degree, campos, prefiltered, debug, num_channels)
+    P, H, W, Cn = inp.P, inp.H, inp.W, inp.C
+    u8 = dict(dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream, ctx = _stream_ctx(dev)
+        # every pixel / every radius is written by the kernels: no zero fill (the reference's
+        # torch::full of out_color is pure waste, rasterize_points.cu:73)
+        out_color = torch.empty((Cn, H, W), dtype=torch.float32, device=dev)
+        out_depth = torch.empty((1, H, W), dtype=torch.float32, device=dev) if want_depth else None
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((lib.sgb_geometry_bytes(P),), **u8)
+        img = torch.empty((lib.sgb_image_bytes(W, H),), **u8)
+        R = C.c_int64(0)
+        _lib.check(lib.sgb_forward_geometry(ctx, C.byref(inp), geom.data_ptr(), radii.data_ptr(), C.byref(R),
+                                            stream), "rasterize_gaussians (geometry)")
+        binning = torch.empty((lib.sgb_binning_bytes(R.value),), **u8)
+        _lib.check(lib.sgb_forward_render(ctx, C.byref(inp), R.value, geom.data_ptr(), binning.data_ptr(),
+                                          img.data_ptr(), radii.data_ptr(), out_color.data_ptr(),
+                                          _ptr(out_depth), stream), "rasterize_gaussians (render)")
+    del keep
+    if want_depth:
+        return int(R.value), out_color, radii, geom, binning, img, out_depth
+    return int(R.value), out_color, radii, geom, binning, img
+
+
+def _backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                   viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer,
+                   R, binningBuffer, imageBuffer, debug, opacities_placeholder=None):
+    lib = _lib.load()
+    Cn, H, W = dL_dout_color.shape  # rasterize_points.cu:146-148
+    dev = means3D.device
+    P = means3D.size(0)
+    # opacities are not an input of Rasterizer::backward (they live in the geometry state); the
+    # struct field only has to be non-null for validation.
+    opac = opacities_placeholder if opacities_placeholder is not None else means3D
+    inp, keep, dev = _make_inputs(background, means3D, colors, opac, scales, rotations, scale_modifier,
+                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh, degree,
+                                  campos, False, debug, Cn)
+    M = inp.M
+    z = dict(dtype=torch.float32, device=dev)
+    dL_dmeans3D = torch.zeros((P, 3), **z)
+    dL_dmeans2D = torch.zeros((P, 3), **z)
+    dL_dcolors = torch.zeros((P, Cn), **z)
+    dL_dconic = torch.zeros((P, 2, 2), **z)
+    dL_dopacity = torch.zeros((P, 1), **z)
+    dL_dcov3D = torch.zeros((P, 6), **z)
+    dL_dsh = torch.zeros((P, M, 3), **z)
+    dL_dscales = torch.zeros((P, 3), **z)
+    dL_drotations = torch.zeros((P, 4), **z)
+    gout = _f32(dL_dout_color, dev, "dL_dout_color")
+    grads = _lib.ViewGrads(
+        dL_dmeans2D=dL_dmeans2D.data_ptr(), dL_dconic=dL_dconic.data_ptr(), dL_dopacity=dL_dopacity.data_ptr(),
+        dL_dcolors=dL_dcolors.data_ptr(), dL_dmeans3D=dL_dmeans3D.data_ptr(), dL_dcov3D=dL_dcov3D.data_ptr(),
+        dL_dsh=dL_dsh.data_ptr() if M > 0 else None, dL_dscales=dL_dscales.data_ptr(),
+        dL_drotations=dL_drotations.data_ptr())
+    if P != 0:
+        with torch.cuda.device(dev):
+            stream, ctx = _stream_ctx(dev)
+            _lib.check(lib.sgb_backward(ctx, C.byref(inp), int(R), radii.data_ptr(), geomBuffer.data_ptr(),
+                                        binningBuffer.data_ptr(), imageBuffer.data_ptr(), gout.data_ptr(),
+                                        C.byref(grads), stream), "rasterize_gaussians_backward")
+    del keep
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def _mark_visible(means3D, viewmatrix, projmatrix):
+    lib = _lib.load()
+    dev = means3D.device
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=dev)
+    if P != 0:
+        m, v, p = _f32(means3D, dev, "positions"), _f32(viewmatrix, dev, "viewmatrix"), _f32(projmatrix, dev, "projmatrix")
+        with torch.cuda.device(dev):
+            stream, _ = _stream_ctx(dev)
+            _lib.check(lib.sgb_mark_visible(P, m.data_ptr(), v.data_ptr(), p.data_ptr(), present.data_ptr(), stream),
+                       "mark_visible")
+    return present
+
+
+class _C_chn:
+    """pybind surface of channel_rasterization._C (rasterize_points.cu:38-223, ext.cpp:16-18)."""
+
+    @staticmethod
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                            viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                            campos, prefiltered, debug, num_channels):
+        return _forward_impl(False, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                             cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                             sh, degree, campos, prefiltered, debug, num_channels)
+
+    @staticmethod
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                     cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
+                                     degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+        return _backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                              viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+                              geomBuffer, R, binningBuffer, imageBuffer, debug)
+
+    mark_visible = staticmethod(_mark_visible)
+
+
+class _C_rgbd:
+    """pybind surface of rgbd_rasterization._C (18 / 20 arguments, forward also returns depth)."""
+
+    @staticmethod
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                            viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                            campos, prefiltered):
+        return _forward_impl(True, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                             cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                             sh, degree, campos, prefiltered, False, 3)
+
+    @staticmethod
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                     cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
+                                     degree, campos, geomBuffer, R, binningBuffer, imageBuffer):
+        return _backward_impl(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                              viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+                              geomBuffer, R, binningBuffer, imageBuffer, False)
+
+    mark_visible = staticmethod(_mark_visible)
+
+
+def _dump(args, path):
+    """Reference debug behaviour without its unconditional CPU deep copy: the argument snapshot is
+    taken only when the native call has already failed (channel_rasterization/__init__.py:86-100)."""
+    try:
+        torch.save(tuple(a.detach().cpu() if isinstance(a, torch.Tensor) else a for a in args), path)
+    except Exception:  # pragma: no cover - best effort
+        pass
+
+
+def make_module(variant: str):
+    """Build (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians,
+    _RasterizeGaussians, _C) for variant 'chn' or 'rgbd'."""
+    assert variant in ("chn", "rgbd")
+    is_chn = variant == "chn"
+    _C = _C_chn if is_chn else _C_rgbd
+
+    if is_chn:
+        class GaussianRasterizationSettings(NamedTuple):  # channel_rasterization/__init__.py:216-229
+            image_height: int
+            image_width: int
+            tanfovx: float
+            tanfovy: float
+            bg: torch.Tensor
+            scale_modifier: float
+            viewmatrix: torch.Tensor
+            projmatrix: torch.Tensor
+            sh_degree: int
+            campos: torch.Tensor
+            prefiltered: bool
+            debug: bool
+            num_channels: int
+    else:
+        class GaussianRasterizationSettings(NamedTuple):  # rgbd_rasterization/__init__.py:159-171
+            image_height: int
+            image_width: int
+            tanfovx: float
+            tanfovy: float
+            bg: torch.Tensor
+            scale_modifier: float
+            viewmatrix: torch.Tensor
+            projmatrix: torch.Tensor
+            sh_degree: int
+            campos: torch.Tensor
+            prefiltered: bool
+            debug: bool
+
+    class _RasterizeGaussians(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                    raster_settings):
+            rs = raster_settings
+            args = [rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                    cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                    rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered]
+            if is_chn:
+                args += [rs.debug, rs.num_channels]
+            try:
+                out = _C.rasterize_gaussians(*args)
+            except Exception:
+                if rs.debug:
+                    _dump(args, "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+            if is_chn:
+                num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = out
+                depth = None
+            else:
+                num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer, depth = out
+            ctx.raster_settings = rs
+            ctx.num_rendered = num_rendered
+            ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+                                  binningBuffer, imgBuffer)
+            ctx.mark_non_differentiable(radii)
+            if is_chn:
+                return color, radii
+            ctx.mark_non_differentiable(depth)  # no depth gradient in the reference (backward ignores it)
+            return color, radii, depth
+
+        @staticmethod
+        def backward(ctx, grad_out_color, *_unused):
+            rs = ctx.raster_settings
+            (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
+             imgBuffer) = ctx.saved_tensors
+            args = [rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                    rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos,
+                    geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer]
+            if is_chn:
+                args.append(rs.debug)
+            try:
+                (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
+                 grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args)
+            except Exception:
+                if rs.debug:
+                    _dump(args, "snapshot_bw.dump")
+                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise
+
+            def present(t, g):  # absent optional inputs were empty tensors; they get no gradient
+                return g if t.numel() != 0 else None
+            return (grad_means3D, grad_means2D, present(sh, grad_sh), present(colors_precomp, grad_colors_precomp),
+                    grad_opacities, present(scales, grad_scales), present(rotations, grad_rotations),
+                    present(cov3Ds_precomp, grad_cov3Ds_precomp), None)
+
+    def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                            raster_settings):
+        return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                         cov3Ds_precomp, raster_settings)
+
+    class GaussianRasterizer(nn.Module):  # channel_rasterization/__init__.py:232-289
+        def __init__(self, raster_settings):
+            super().__init__()
+            self.raster_settings = raster_settings
+
+        def markVisible(self, positions):
+            with torch.no_grad():
+                rs = self.raster_settings
+                return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+        def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3D_precomp=None):
+            rs = self.raster_settings
+            if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+                raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+            if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                    (scales is not None or rotations is not None) and cov3D_precomp is not None):
+                raise Exception(
+                    "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+            empty = torch.Tensor([])
+            shs = empty if shs is None else shs
+            colors_precomp = empty if colors_precomp is None else colors_precomp
+            scales = empty if scales is None else scales
+            rotations = empty if rotations is None else rotations
+            cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+            return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                       cov3D_precomp, rs)
+
+    GaussianRasterizationSettings.__qualname__ = "GaussianRasterizationSettings"
+    GaussianRasterizer.__qualname__ = "GaussianRasterizer"
+    return GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _RasterizeGaussians, _C
