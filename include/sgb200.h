@@ -100,6 +100,18 @@ void sgb_ctx_destroy(sgb_ctx* ctx);
 /* Bytes of device scratch the ctx currently holds (diagnostics). */
 size_t sgb_ctx_scratch_bytes(const sgb_ctx* ctx);
 
+/* Stage tracing: when enabled, every stage of the calls made through this ctx is bracketed by a
+ * CUDA event pair on the caller's stream.  sgb_profile_read synchronises those events and returns,
+ * per stage, the summed milliseconds and the number of intervals since the previous read
+ * (arrays of sgb_profile_num_stages() entries).  At most 128 intervals per stage are kept. */
+int sgb_profile_enable(sgb_ctx* ctx, int on);
+int sgb_profile_read(sgb_ctx* ctx, float* ms_sum, int32_t* count);
+int sgb_profile_num_stages(void);
+const char* sgb_profile_stage_name(int stage);
+/* Kernels of this library launched through ctx so far (library_calls = 0), or the number of
+ * CUB device-wide calls (library_calls = 1; each is several kernels). */
+uint64_t sgb_ctx_launch_count(const sgb_ctx* ctx, int library_calls);
+
 /* Sizes of the three caller-owned state buffers (multiples of 256 B). */
 size_t sgb_geometry_bytes(int32_t P);
 size_t sgb_binning_bytes(int64_t num_rendered);

@@ -52,7 +52,8 @@ EXPORTS = (
     "sgb_last_error", "sgb_version", "sgb_ctx_create", "sgb_ctx_destroy", "sgb_ctx_scratch_bytes",
     "sgb_geometry_bytes", "sgb_binning_bytes", "sgb_image_bytes", "sgb_forward_geometry",
     "sgb_forward_render", "sgb_backward", "sgb_mark_visible", "sgb_state_field", "sgb_fusion_map",
-    "sgb_fusion_accumulate", "sgb_fusion_normalize",
+    "sgb_fusion_accumulate", "sgb_fusion_normalize", "sgb_profile_enable", "sgb_profile_read",
+    "sgb_profile_num_stages", "sgb_profile_stage_name", "sgb_ctx_launch_count",
 )
 
 _lib = None
@@ -96,6 +97,12 @@ def load() -> C.CDLL:
         lib.sgb_fusion_map.argtypes = [vp, C.POINTER(FusionView), vp, vp]
         lib.sgb_fusion_accumulate.argtypes = [vp, C.POINTER(FusionView), vp, i32, i32, vp, vp, vp, vp]
         lib.sgb_fusion_normalize.argtypes = [i32, i32, vp, vp, vp]
+        lib.sgb_profile_enable.argtypes = [vp, C.c_int]
+        lib.sgb_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+        lib.sgb_profile_stage_name.argtypes = [C.c_int]
+        lib.sgb_profile_stage_name.restype = C.c_char_p
+        lib.sgb_ctx_launch_count.argtypes = [vp, C.c_int]
+        lib.sgb_ctx_launch_count.restype = C.c_uint64
         _lib = lib
         return lib
 
@@ -119,3 +126,22 @@ def ctx_for(device_index: int, stream_handle: int) -> int:
         h = out.value
         _ctxs[key] = h
     return h
+
+
+def profile_enable(ctx: int, on: bool = True) -> None:
+    check(load().sgb_profile_enable(ctx, int(on)), "sgb_profile_enable")
+
+
+def profile_read(ctx: int) -> dict:
+    """{stage name: (summed ms, intervals)} since the previous read."""
+    lib = load()
+    n = lib.sgb_profile_num_stages()
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(lib.sgb_profile_read(ctx, ms, cnt), "sgb_profile_read")
+    return {lib.sgb_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+
+def launch_count(ctx: int) -> tuple:
+    lib = load()
+    return int(lib.sgb_ctx_launch_count(ctx, 0)), int(lib.sgb_ctx_launch_count(ctx, 1))

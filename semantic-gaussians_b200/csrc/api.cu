@@ -86,11 +86,60 @@ int sgb_ctx_create(sgb_ctx** out, int device) {
 
 void sgb_ctx_destroy(sgb_ctx* c) {
     if (!c) return;
+    if (c->prof.created)
+        for (int st = 0; st < ST_COUNT; st++)
+            for (int i = 0; i < kProfRing; i++) {
+                cudaEventDestroy(c->prof.ev[st][i][0]);
+                cudaEventDestroy(c->prof.ev[st][i][1]);
+            }
     if (c->geom.p) cudaFree(c->geom.p);
     if (c->bin.p) cudaFree(c->bin.p);
     if (c->misc.p) cudaFree(c->misc.p);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
+}
+
+int sgb_profile_enable(sgb_ctx* c, int on) {
+    if (!c) { set_error("null ctx"); return SGB_E_INVALID; }
+    if (on && !c->prof.created) {
+        for (int st = 0; st < ST_COUNT; st++)
+            for (int i = 0; i < kProfRing; i++) {
+                SGB_CUDA(cudaEventCreate(&c->prof.ev[st][i][0]));
+                SGB_CUDA(cudaEventCreate(&c->prof.ev[st][i][1]));
+            }
+        c->prof.created = true;
+    }
+    for (int st = 0; st < ST_COUNT; st++) c->prof.n[st] = 0;
+    c->prof.on = on != 0;
+    return SGB_OK;
+}
+
+int sgb_profile_read(sgb_ctx* c, float* ms_sum, int32_t* count) {
+    if (!c || !ms_sum || !count) { set_error("null argument"); return SGB_E_INVALID; }
+    for (int st = 0; st < ST_COUNT; st++) {
+        float acc = 0.f;
+        for (int i = 0; i < c->prof.n[st]; i++) {
+            SGB_CUDA(cudaEventSynchronize(c->prof.ev[st][i][1]));
+            float ms = 0.f;
+            SGB_CUDA(cudaEventElapsedTime(&ms, c->prof.ev[st][i][0], c->prof.ev[st][i][1]));
+            acc += ms;
+        }
+        ms_sum[st] = acc;
+        count[st] = c->prof.n[st];
+        c->prof.n[st] = 0;
+    }
+    return SGB_OK;
+}
+
+int sgb_profile_num_stages(void) { return ST_COUNT; }
+const char* sgb_profile_stage_name(int st) {
+    static const char* names[ST_COUNT] = {"preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges",
+                                          "blend_fwd", "blend_bwd", "geom_bwd", "fusion_project",
+                                          "fusion_transpose", "fusion_gather"};
+    return (st >= 0 && st < ST_COUNT) ? names[st] : "";
+}
+uint64_t sgb_ctx_launch_count(const sgb_ctx* c, int library_calls) {
+    return c ? (library_calls ? c->lib_launches : c->launches) : 0;
 }
 
 size_t sgb_ctx_scratch_bytes(const sgb_ctx* c) { return c ? c->geom.cap + c->bin.cap + c->misc.cap : 0; }
@@ -139,6 +188,8 @@ int sgb_forward_render(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rend
     rc = run_binning(ctx, *in, num_rendered, g, b, im, radii, s);
     if (rc) return rc;
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:324
+    StageTimer t(ctx, ST_BLEND_FWD, s);
+    ctx->launches += 1;
     return launch_blend_forward(*in, g, b, im, colors, out_color, out_depth, s);
 }
 
@@ -160,11 +211,15 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
     ImgView im = ImgView::carve(const_cast<void*>(image_state), in->W, in->H);
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:394
     if (num_rendered > 0) {
+        StageTimer t(ctx, ST_BLEND_BWD, s);
+        ctx->launches += 1;
         rc = launch_blend_backward(*in, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity,
                                    gr->dL_dcolors, s);
         if (rc) return rc;
     }
     const float* cov3D = in->cov3D_precomp ? in->cov3D_precomp : g.cov3D;  // rasterizer_impl.cu:417
+    StageTimer t(ctx, ST_GEOM_BWD, s);
+    ctx->launches += 1;
     return launch_geom_backward(*in, g, radii, cov3D, gr->dL_dcolors, *gr, s);
 }
 

@@ -151,12 +151,23 @@ int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g
     uint32_t* offsets = (uint32_t*)(base + 4 * arr);
     void* cub_tmp = base + 5 * arr;
 
-    rc = launch_preprocess(in, g, radii, keys_in, s);
-    if (rc) return rc;
-    iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vals_in);
-    SGB_LAUNCH_CHECK("iota_kernel", in.debug, s);
-    SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_in, keys_out, vals_in, perm, P, 0, 32, s));
     {
+        StageTimer t(ctx, ST_PREPROCESS, s);
+        rc = launch_preprocess(in, g, radii, keys_in, s);
+        if (rc) return rc;
+        ctx->launches += 1;
+    }
+    {
+        StageTimer t(ctx, ST_DEPTH_SORT, s);
+        iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vals_in);
+        SGB_LAUNCH_CHECK("iota_kernel", in.debug, s);
+        SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_in, keys_out, vals_in, perm, P, 0, 32, s));
+        ctx->launches += 1;
+        ctx->lib_launches += 1;
+    }
+    {
+        StageTimer t(ctx, ST_SCAN, s);
+        ctx->lib_launches += 1;
         cub::CountingInputIterator<uint32_t> cnt(0);
         PermutedCount op{perm, g.tiles_touched};
         cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> it(cnt, op);
@@ -195,13 +206,25 @@ int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, 
     uint32_t* vals_unsorted = (uint32_t*)(base + 2 * arr);
     void* cub_tmp = base + 3 * arr;
 
-    emit_instances_kernel<<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
-                                                            tile_grid, keys_unsorted, vals_unsorted);
-    SGB_LAUNCH_CHECK("emit_instances_kernel", in.debug, s);
-    SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_unsorted, keys_sorted, vals_unsorted,
-                                             b.point_list, R, 0, bits, s));
-    identify_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, im.ranges);
-    SGB_LAUNCH_CHECK("identify_ranges_kernel", in.debug, s);
+    {
+        StageTimer t(ctx, ST_EMIT, s);
+        emit_instances_kernel<<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
+                                                                tile_grid, keys_unsorted, vals_unsorted);
+        SGB_LAUNCH_CHECK("emit_instances_kernel", in.debug, s);
+        ctx->launches += 1;
+    }
+    {
+        StageTimer t(ctx, ST_TILE_SORT, s);
+        SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_unsorted, keys_sorted, vals_unsorted,
+                                                 b.point_list, R, 0, bits, s));
+        ctx->lib_launches += 1;
+    }
+    {
+        StageTimer t(ctx, ST_RANGES, s);
+        identify_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, im.ranges);
+        SGB_LAUNCH_CHECK("identify_ranges_kernel", in.debug, s);
+        ctx->launches += 1;
+    }
     return SGB_OK;
 }
 

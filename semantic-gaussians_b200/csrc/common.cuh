@@ -100,8 +100,28 @@ struct Scratch {
 
 }  // namespace sgb
 
+namespace sgb {
+// Built-in stage tracing (the reference has none; its only timing hook is train.py's per-iteration
+// event pair).  When enabled, every stage is bracketed by a CUDA event pair recorded on the
+// caller's stream; sgb_profile_read() sums the pairs recorded since the last read.
+enum Stage {
+    ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
+    ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_TRANSPOSE, ST_FUSION_GATHER, ST_COUNT
+};
+constexpr int kProfRing = 128;
+struct Profiler {
+    bool on = false;
+    cudaEvent_t ev[ST_COUNT][kProfRing][2];
+    int n[ST_COUNT];
+    bool created = false;
+};
+}  // namespace sgb
+
 struct sgb_ctx {
     int device = 0;
+    sgb::Profiler prof;
+    uint64_t launches = 0;       // kernels of this library launched through this ctx
+    uint64_t lib_launches = 0;   // CUB device-wide calls (each several kernels)
     sgb::Scratch geom;     // depth-sort keys/values, offsets, CUB temp
     sgb::Scratch bin;      // unsorted / sorted tile keys, unsorted values, CUB temp
     sgb::Scratch misc;     // fusion: transposed feature map, z-buffer
@@ -113,6 +133,19 @@ struct sgb_ctx {
 };
 
 namespace sgb {
+
+struct StageTimer {  // RAII event pair around one stage
+    sgb_ctx* c; int st; cudaStream_t s; int slot;
+    StageTimer(sgb_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), st(stage), s(stream), slot(-1) {
+        if (c && c->prof.on && c->prof.n[st] < kProfRing) {
+            slot = c->prof.n[st]++;
+            cudaEventRecord(c->prof.ev[st][slot][0], s);
+        }
+    }
+    ~StageTimer() {
+        if (slot >= 0) cudaEventRecord(c->prof.ev[st][slot][1], s);
+    }
+};
 
 // ------------------------------------------------------------------ stage launchers
 int launch_preprocess(const sgb_view_inputs& in, GeomView g, int32_t* radii, uint32_t* depth_keys,

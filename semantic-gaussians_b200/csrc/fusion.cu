@@ -251,18 +251,29 @@ extern "C" int sgb_fusion_accumulate(sgb_ctx* ctx, const sgb_fusion_view* v, con
     void* featT = extra;
     int* pix_of = (int*)(extra + tbytes);
 
-    fusion_pix_kernel<<<(v->P + 255) / 256, 256, 0, s>>>(*v, zbuf, pix_of, count, n_visible_dev);
-    SGB_LAUNCH_CHECK("fusion_pix_kernel", 0, s);
+    {
+        StageTimer t(ctx, ST_FUSION_PROJECT, s);
+        fusion_pix_kernel<<<(v->P + 255) / 256, 256, 0, s>>>(*v, zbuf, pix_of, count, n_visible_dev);
+        SGB_LAUNCH_CHECK("fusion_pix_kernel", 0, s);
+    }
     dim3 tgrid((unsigned)((npix + 31) / 32), (unsigned)((C + 31) / 32)), tblock(32, 8);
     const int gblocks = 148 * 8;
-    if (feat_dtype == SGB_FEAT_F16) {
-        transpose_kernel<__half><<<tgrid, tblock, 0, s>>>((const __half*)features, (__half*)featT, C, (int)npix);
-        fusion_gather_kernel<__half><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const __half*)featT, feat_sum);
-    } else {
-        transpose_kernel<float><<<tgrid, tblock, 0, s>>>((const float*)features, (float*)featT, C, (int)npix);
-        fusion_gather_kernel<float><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const float*)featT, feat_sum);
+    {
+        StageTimer t(ctx, ST_FUSION_TRANSPOSE, s);
+        if (feat_dtype == SGB_FEAT_F16)
+            transpose_kernel<__half><<<tgrid, tblock, 0, s>>>((const __half*)features, (__half*)featT, C, (int)npix);
+        else
+            transpose_kernel<float><<<tgrid, tblock, 0, s>>>((const float*)features, (float*)featT, C, (int)npix);
+    }
+    {
+        StageTimer t(ctx, ST_FUSION_GATHER, s);
+        if (feat_dtype == SGB_FEAT_F16)
+            fusion_gather_kernel<__half><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const __half*)featT, feat_sum);
+        else
+            fusion_gather_kernel<float><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const float*)featT, feat_sum);
     }
     SGB_LAUNCH_CHECK("fusion_gather_kernel", 0, s);
+    ctx->launches += 3;
     return SGB_OK;
 }
 
