@@ -74,20 +74,28 @@ def mark_visible(means3D, viewmatrix):
     return present.astype(bool)
 
 
-def bin_instances(pre, W, H):
-    """rasterizer_impl.cu:70-138, 277-321 → point_list (R,), keys (R,) u64, ranges (tiles,2)."""
+def bin_instances(pre, W, H, tile_rows=None):
+    """rasterizer_impl.cu:70-138, 277-321 → point_list (R,), keys (R,) u64, ranges (tiles,2).
+    tile_rows=(r0, r1) restricts emission to those tile rows (bench.py's bounded CPU sample)."""
     P = pre["radii"].shape[0]
-    R = int(lib().orc_count_instances(C.c_int(P), _p(pre["tiles_touched"])))
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    point_list = np.zeros(max(R, 1), np.uint32)
-    keys = np.zeros(max(R, 1), np.uint64)
+    r0, r1 = tile_rows if tile_rows is not None else (0, 0)
+    if tile_rows is None:
+        cap = int(lib().orc_count_instances(C.c_int(P), _p(pre["tiles_touched"])))
+    else:  # upper bound: every visible Gaussian's rect width times the band height
+        rect = pre["rect"]
+        y0 = np.maximum(rect[:, 1], r0)
+        y1 = np.minimum(rect[:, 3], r1)
+        cap = int((np.maximum(y1 - y0, 0).astype(np.int64) * (rect[:, 2] - rect[:, 0])).sum())
+    point_list = np.zeros(max(cap, 1), np.uint32)
+    keys = np.zeros(max(cap, 1), np.uint64)
     ranges = np.zeros((tiles, 2), np.uint32)
-    lib().orc_bin(C.c_int(P), C.c_int(W), C.c_int(H), _p(pre["radii"]), _p(pre["means2D"]), _p(pre["depths"]),
-                  _p(pre["tiles_touched"]), _p(point_list), _p(keys), _p(ranges))
+    R = int(lib().orc_bin(C.c_int(P), C.c_int(W), C.c_int(H), _p(pre["radii"]), _p(pre["means2D"]), _p(pre["depths"]),
+                          _p(pre["tiles_touched"]), _p(point_list), _p(keys), _p(ranges), C.c_int(r0), C.c_int(r1)))
     return dict(R=R, point_list=point_list[:R], keys=keys[:R], ranges=ranges)
 
 
-def render_forward(pre, binning, features, bg, W, H, want_depth=False):
+def render_forward(pre, binning, features, bg, W, H, want_depth=False, rows=(0, 0)):
     features = _f32(features)
     Cn = features.shape[1]
     bg = _f32(bg).reshape(-1)
@@ -99,7 +107,7 @@ def render_forward(pre, binning, features, bg, W, H, want_depth=False):
     pl = binning["point_list"] if binning["R"] > 0 else np.zeros(1, np.uint32)
     lib().orc_render_forward(C.c_int(W), C.c_int(H), C.c_int(Cn), _p(binning["ranges"]), _p(pl), _p(pre["means2D"]),
                              _p(features), _p(pre["conic_opacity"]), _p(pre["depths"]), _p(bg), _p(out_color),
-                             _p(final_T), _p(n_contrib), _p(out_depth), _p(fragile))
+                             _p(final_T), _p(n_contrib), _p(out_depth), _p(fragile), C.c_int(rows[0]), C.c_int(rows[1]))
     return dict(color=out_color, final_T=final_T, n_contrib=n_contrib, depth=out_depth,
                 fragile=fragile.reshape(H, W).astype(bool))
 
@@ -120,7 +128,7 @@ def forward(scene_arrays: dict, cam: dict, W: int, H: int, bg, features=None, wa
 
 
 def backward(fwd: dict, scene_arrays: dict, cam: dict, W: int, H: int, bg, dL_dpix, features=None, sh_degree=3,
-             scale_modifier=1.0):
+             scale_modifier=1.0, rows=(0, 0)):
     """backward.cu: blend backward + per-Gaussian backward.  Returns the reference's gradient set
     (float64 for the four accumulated-by-atomics quantities, float32 for the per-Gaussian chain,
     which consumes them rounded to float32 like the reference's buffers)."""
@@ -137,7 +145,8 @@ def backward(fwd: dict, scene_arrays: dict, cam: dict, W: int, H: int, bg, dL_dp
     pl = b["point_list"] if b["R"] > 0 else np.zeros(1, np.uint32)
     lib().orc_render_backward(C.c_int(W), C.c_int(H), C.c_int(Cn), _p(b["ranges"]), _p(pl), _p(bg),
                               _p(pre["means2D"]), _p(pre["conic_opacity"]), _p(colors), _p(fwd["final_T"]),
-                              _p(fwd["n_contrib"]), _p(dL_dpix), _p(g_mean2D), _p(g_conic), _p(g_opac), _p(g_colors))
+                              _p(fwd["n_contrib"]), _p(dL_dpix), _p(g_mean2D), _p(g_conic), _p(g_opac), _p(g_colors),
+                              C.c_int(rows[0]), C.c_int(rows[1]))
     shs = _f32(scene_arrays.get("shs")) if features is None else None
     M = shs.shape[1] if shs is not None else 0
     scales, rots = _f32(scene_arrays.get("scales")), _f32(scene_arrays.get("rotations"))
