@@ -71,12 +71,18 @@ def test_fusion_edge_cases():
     scene, cams, feats, _ = fusion_inputs(seed=4, P=500, w=64, h=48, C=8, nviews=1)
     cam = cams[0]
     mapper = PointCloudToImageMapper([64, 48], 0.05, 0, cam.intrinsics(), device=dev)
-    # a point exactly at the camera centre (z = 0 -> inf/nan pixel) and one behind the camera
+    # a point (numerically) at the camera centre and one behind the camera
     pts = np.concatenate([scene.xyz, cam.camera_center[None], (2 * cam.camera_center)[None]]).astype(np.float32)
     m, _ = mapper.compute_mapping(cam.world_view_transform, pts, None)
     K = fo.rescale_intrinsics(cam.intrinsics(), [64, 48])
     want = fo.compute_mapping(cam.world_view_transform, pts, [64, 48], K, 0.05, 0, None)
-    assert np.array_equal(m, want) and m[-1, 2] == 0 and m[-2, 2] == 0
+    assert np.array_equal(m, want) and m[-1, 2] == 0
+    # exact z = 0 (0/0 and x/0 -> nan / inf pixel coordinates) with an identity camera
+    ident = np.eye(4, dtype=np.float32)
+    pts0 = np.array([[0, 0, 0], [1, 0, 0], [0, -2, 0], [0.1, 0.1, 1.0], [0, 0, -1]], np.float32)
+    m0, _ = mapper.compute_mapping(ident, pts0, None)
+    want0 = fo.compute_mapping(ident, pts0, [64, 48], K, 0.05, 0, None)
+    assert np.array_equal(m0, want0) and list(m0[:, 2]) == [0, 0, 0, 1, 0]
     # empty point set
     m0, _ = mapper.compute_mapping(cam.world_view_transform, np.zeros((0, 3), np.float32), None)
     assert m0.shape == (0, 3)

@@ -135,7 +135,8 @@ def test_oracle_pinned_to_reference_golden_k1():
     both = vis & (pre["radii"] > 0)
     np.testing.assert_allclose(pre["means2D"][both], gold["k1_means2D"][both], rtol=2e-6, atol=2e-4)
     np.testing.assert_allclose(pre["conic_opacity"][both], gold["k1_conic_opacity"][both], rtol=2e-4, atol=1e-7)
-    np.testing.assert_array_equal(pre["depths"][both].view(np.int32) // 8, gold["k1_depths"][both].view(np.int32) // 8)
+    ulp = np.abs(pre["depths"][both].view(np.int32).astype(np.int64) - gold["k1_depths"][both].view(np.int32))
+    assert ulp.max() <= 4                       # view-space depth: a 4-term dot product, contraction differences only
     np.testing.assert_allclose(pre["rgb"][both], gold["k1_rgb"][both], rtol=1e-5, atol=1e-6)
     assert (pre["tiles_touched"] != gold["k1_tiles_touched"].view(np.uint32)).sum() <= 5
     if f["bin"]["R"] == int(gold["k1_R"]):
