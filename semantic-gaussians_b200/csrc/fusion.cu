@@ -195,7 +195,7 @@ int prepare_zbuf(sgb_ctx* ctx, const sgb_fusion_view& v, size_t extra, double** 
 }
 
 int check_view(const sgb_fusion_view* v) {
-    if (!v || v->P < 0 || !v->xyz || !v->world_to_camera || v->w <= 0 || v->h <= 0) {
+    if (!v || v->P < 0 || (v->P > 0 && !v->xyz) || !v->world_to_camera || v->w <= 0 || v->h <= 0) {
         set_error("fusion view: null pointer or non-positive size");
         return SGB_E_INVALID;
     }

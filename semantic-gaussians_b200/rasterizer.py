@@ -79,6 +79,17 @@ def _forward_impl(want_depth: bool, background, means3D, colors, opacity, scales
                   cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
                   degree, campos, prefiltered, debug, num_channels):
     lib = _lib.load()
+    if means3D.ndimension() == 2 and means3D.size(0) == 0 and means3D.is_cuda:
+        # Empty scene: the reference never enters the native forward (rasterize_points.cu:84) and
+        # returns its zero-initialised outputs — zeros, not the background.
+        dev = means3D.device
+        z = torch.zeros((num_channels, image_height, image_width), dtype=torch.float32, device=dev)
+        e8 = torch.empty((0,), dtype=torch.uint8, device=dev)
+        radii = torch.zeros((0,), dtype=torch.int32, device=dev)
+        img = torch.zeros((lib.sgb_image_bytes(image_width, image_height),), dtype=torch.uint8, device=dev)
+        if want_depth:
+            return 0, z, radii, e8, e8.clone(), img, torch.zeros((1, image_height, image_width), device=dev)
+        return 0, z, radii, e8, e8.clone(), img
     inp, keep, dev = _make_inputs(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                                   cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                                   image_width, sh, degree, campos, prefiltered, debug, num_channels)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 K1 = dict(P=10000, W=256, H=256, seed=0)
-KF = dict(P=3000, W=96, H=64, C=100, seed=11)        # feature raster (chn / chn_c100)
+KF = dict(P=3000, W=64, H=48, C=100, seed=11)        # feature raster (chn / chn_c100)
 
 
 def golden_inputs(kind):

@@ -236,11 +236,11 @@ def test_empty_and_degenerate_inputs():
     def rs(C):
         return chn.GaussianRasterizationSettings(48, 64, cm["tanfovx"], cm["tanfovy"], torch.full((C,), 0.5, device=dev),
                                                  1.0, cm["viewmatrix"], cm["projmatrix"], 0, cm["campos"], False, False, C)
-    # P = 0: background only
+    # P = 0: the reference skips the native call and returns its zero-filled image (rasterize_points.cu:73,84)
     z = lambda *s: torch.zeros(s, device=dev)
     color, radii = chn.GaussianRasterizer(rs(8))(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1),
                                                  colors_precomp=z(0, 8), scales=z(0, 3), rotations=z(0, 4))
-    assert color.shape == (8, 48, 64) and radii.numel() == 0 and torch.all(color == 0.5)
+    assert color.shape == (8, 48, 64) and radii.numel() == 0 and torch.all(color == 0.0)
     # everything behind the camera: nothing rendered, R = 0
     xyz = torch.tensor([[0.0, 0.0, 0.0]], device=dev) + torch.as_tensor(cam.camera_center, device=dev) * 2
     color, radii = chn.GaussianRasterizer(rs(4))(means3D=xyz, means2D=z(1, 3), opacities=torch.ones(1, 1, device=dev),
