@@ -219,8 +219,8 @@ extern "C" int sgb_fusion_map(sgb_ctx* ctx, const sgb_fusion_view* v, int64_t* m
     cudaStream_t s = (cudaStream_t)stream;
     int rc = check_view(v);
     if (rc) return rc;
-    if (!ctx || !mapping) { set_error("sgb_fusion_map: null ctx/mapping"); return SGB_E_INVALID; }
     if (v->P == 0) return SGB_OK;
+    if (!ctx || !mapping) { set_error("sgb_fusion_map: null ctx/mapping"); return SGB_E_INVALID; }
     double* zbuf; char* extra;
     rc = prepare_zbuf(ctx, *v, 0, &zbuf, &extra, s);
     if (rc) return rc;
