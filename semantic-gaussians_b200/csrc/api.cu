@@ -1,5 +1,6 @@
 // C-ABI entry points (include/sgb200.h): argument validation, state carving, stage sequencing.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -95,6 +96,7 @@ void sgb_ctx_destroy(sgb_ctx* c) {
     if (c->geom.p) cudaFree(c->geom.p);
     if (c->bin.p) cudaFree(c->bin.p);
     if (c->misc.p) cudaFree(c->misc.p);
+    if (c->pool.p) cudaFree(c->pool.p);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -135,14 +137,14 @@ int sgb_profile_num_stages(void) { return ST_COUNT; }
 const char* sgb_profile_stage_name(int st) {
     static const char* names[ST_COUNT] = {"preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges",
                                           "blend_fwd", "blend_bwd", "geom_bwd", "fusion_project",
-                                          "fusion_transpose", "fusion_gather"};
+                                          "fusion_transpose", "fusion_gather", "alpha_pass", "dfeature"};
     return (st >= 0 && st < ST_COUNT) ? names[st] : "";
 }
 uint64_t sgb_ctx_launch_count(const sgb_ctx* c, int library_calls) {
     return c ? (library_calls ? c->lib_launches : c->launches) : 0;
 }
 
-size_t sgb_ctx_scratch_bytes(const sgb_ctx* c) { return c ? c->geom.cap + c->bin.cap + c->misc.cap : 0; }
+size_t sgb_ctx_scratch_bytes(const sgb_ctx* c) { return c ? c->geom.cap + c->bin.cap + c->misc.cap + c->pool.cap : 0; }
 
 size_t sgb_geometry_bytes(int32_t P) { return GeomView::carve(nullptr, P > 0 ? P : 1).bytes; }
 size_t sgb_binning_bytes(int64_t R) { return BinView::carve(nullptr, R).bytes; }
@@ -188,6 +190,9 @@ int sgb_forward_render(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rend
     rc = run_binning(ctx, *in, num_rendered, g, b, im, radii, s);
     if (rc) return rc;
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:324
+    const char* impl = getenv("SGB_BLEND_IMPL");  // diagnostics: "v2" = fused chain+accumulate per chunk
+    if (in->C > 4 && !out_depth && !(impl && impl[0] == 'v' && impl[1] == '2'))
+        return blend_forward_v3(ctx, *in, num_rendered, g, b, im, colors, out_color, s);
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
     return launch_blend_forward(*in, g, b, im, colors, out_color, out_depth, s);
@@ -210,7 +215,12 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
     BinView b = BinView::carve(const_cast<void*>(binning_state), num_rendered);
     ImgView im = ImgView::carve(const_cast<void*>(image_state), in->W, in->H);
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:394
-    if (num_rendered > 0) {
+    const char* impl = getenv("SGB_BLEND_IMPL");
+    if (num_rendered > 0 && in->C > 4 && !(impl && impl[0] == 'v' && impl[1] == '2')) {
+        rc = blend_backward_v3(ctx, *in, num_rendered, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic,
+                               gr->dL_dopacity, gr->dL_dcolors, s);
+        if (rc) return rc;
+    } else if (num_rendered > 0) {
         StageTimer t(ctx, ST_BLEND_BWD, s);
         ctx->launches += 1;
         rc = launch_blend_backward(*in, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity,

@@ -1,0 +1,1505 @@
+// C-channel blend, "weights once" pipeline (C > 4).
+//
+// Measured on the K3 scene (1 M Gaussians, 1080p): a tile walks ~280 list entries before all its
+// pixels saturate, but only ~115 of them touch any pixel of the tile (the reference bins by the
+// 3-sigma square of the major axis, rasterizer_impl.cu:91 / forward.cu:229-235), and the scalar
+// alpha / transmittance chain costs about as many issue slots as a 64-channel accumulation.  A
+// kernel that fuses chain and accumulation per channel chunk (blend_fwd.cu / blend_bwd.cu v2)
+// therefore spends most of its instructions re-deriving the same weights in every chunk, forward
+// and backward.  Here the chain runs ONCE per view:
+//
+//   alpha_pass        one CTA per tile, thread = pixel: the reference's chain verbatim
+//                     (forward.cu:326-363) -> final_T, n_contrib, and for every Gaussian that
+//                     touches the tile a 1 KB row of weights w[pixel] = alpha * T (0 where the
+//                     pixel skips it) appended to a per-tile linked list of 16-entry chunks.
+//   blend_forward_v3  CTA = (tile, 64-channel chunk), barrier-free: each warp streams the tile's
+//                     weight rows and feature slices straight from L2 and accumulates an
+//                     8 px x 8 ch register micro-tile per lane (outer product, packed FMA).
+//   chain_backward_v3 CTA = tile: s = <feature, dL/dout> per (pixel, Gaussian) for all channels
+//                     (register micro-tiles + transposed shuffle reduce), then the reference's
+//                     back-to-front chain (backward.cu:477-550) in dot-product form -> dL/dmean2D,
+//                     dL/dconic, dL/dopacity.
+//   dfeature_v3       CTA = (tile, 64-channel chunk): dL/dfeature[g][ch] = sum_px w * dL/dout, one
+//                     warp per 8-channel slice over all 256 pixels, one 32-byte reduction per
+//                     (Gaussian, tile, slice).
+//
+// Results are unchanged: the integer outputs come from the verbatim chain; every accumulator still
+// adds its Gaussians in depth order.
+#include <cstdlib>
+#include "common.cuh"
+
+namespace sgb {
+
+namespace {
+
+constexpr int kThreads = SGB_TILE_PIX;
+constexpr int kChunkEntries = 16;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct __align__(16) WChunk {
+    uint32_t next, prev, pad0, pad1;
+    uint2 meta[kChunkEntries];             // x: Gaussian id, y: bit w = strip (warp) w has a non-zero weight
+    float w[kChunkEntries][SGB_TILE_PIX];  // alpha * T per pixel (tile-local index ty*16+tx)
+};
+static_assert(sizeof(WChunk) % 16 == 0, "WChunk must keep 16-byte alignment in an array");
+
+struct PoolHdr {
+    uint32_t counter;   // chunks handed out (keeps counting past capacity: the true demand)
+    uint32_t overflow;  // set when counter ran past capacity (results invalid, caller retries)
+};
+
+struct PoolView {
+    PoolHdr* hdr;
+    uint32_t* head;   // [tiles] first chunk or kNone
+    uint32_t* tail;   // [tiles] last chunk or kNone
+    uint32_t* count;  // [tiles] entries
+    WChunk* chunks;
+    uint32_t capacity;
+};
+
+template <int N>
+__device__ __forceinline__ void xreduce_step(float (&v)[8], int lane, int step) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+        const float send = upper ? v[i] : v[i + N / 2];
+        const float keep = upper ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+}
+
+// ------------------------------------------------------------------------------------ alpha pass
+constexpr int kAB = 32;  // list entries per staging round
+
+struct __align__(16) AlphaSmem {
+    float4 recA[kAB];
+    float4 recB[kAB];
+    uint32_t ids[kAB];
+    float wbuf[kAB][SGB_TILE_PIX];
+    uint32_t wmask[8];
+    uint32_t slot_chunk[kAB];
+    uint32_t cur_chunk;
+    uint32_t s_last;
+};
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const SplatRec* __restrict__ rec, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+    uint32_t* __restrict__ tile_last, float* __restrict__ out_depth, PoolView pool) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    AlphaSmem& sm = *reinterpret_cast<AlphaSmem*>(smem_raw);
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
+    const uint2 pix = {(uint32_t)(tile % tiles_x) * SGB_TILE + tx, (uint32_t)(tile / tiles_x) * SGB_TILE + ty};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    bool done = !inside;
+
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const int nbatches = (total + kAB - 1) / kAB;
+    if (tid == 0) { sm.cur_chunk = kNone; sm.s_last = 0; }
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float D = 15.0f;
+    uint32_t n_tile = 0;  // entries appended so far (uniform)
+
+    for (int b = 0; b < nbatches; b++) {
+        const int num_done = __syncthreads_count(done);  // forward.cu:310-312
+        if (num_done == kThreads) break;
+        const int base = b * kAB;
+        const int cnt = min(kAB, total - base);
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + base + tid];
+            sm.ids[tid] = id;
+            const float4* rp = reinterpret_cast<const float4*>(rec + id);
+            sm.recA[tid] = __ldg(rp);
+            sm.recB[tid] = __ldg(rp + 1);
+        }
+        __syncthreads();
+        uint32_t my_mask = 0;
+        for (int j = 0; j < cnt; j++) {
+            float w = 0.f;
+            if (!done) {
+                // forward.cu:333-362 verbatim
+                const float4 a = sm.recA[j];
+                const float2 xy = {a.x, a.y};
+                const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+                const float4 con_o = sm.recB[j];
+                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                if (!(power > 0.0f)) {
+                    const float alpha = min(0.99f, con_o.w * exp(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = T * (1 - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            w = alpha * T;
+                            if (DEPTH) {
+                                if (T > 0.5f && test_T < 0.5) D = a.z;
+                            }
+                            T = test_T;
+                            last_contributor = (uint32_t)(base + j + 1);
+                        }
+                    }
+                }
+            }
+            sm.wbuf[j][tid] = w;
+            if (__ballot_sync(0xffffffffu, w != 0.f)) my_mask |= 1u << j;
+        }
+        if (lane == 0) sm.wmask[warp] = my_mask;
+        __syncthreads();
+        uint32_t tm = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) tm |= sm.wmask[q];
+        const int n_act = __popc(tm);
+        if (n_act) {
+            if (tid == 0) {
+                uint32_t e = n_tile, cur = sm.cur_chunk;
+                for (int k = 0; k < n_act; k++, e++) {
+                    if ((e & (kChunkEntries - 1)) == 0) {
+                        uint32_t nw = atomicAdd(&pool.hdr->counter, 1u);
+                        if (nw >= pool.capacity) {
+                            pool.hdr->overflow = 1;
+                            nw = pool.capacity - 1;
+                        }
+                        pool.chunks[nw].prev = cur;
+                        pool.chunks[nw].next = kNone;
+                        if (cur == kNone) pool.head[tile] = nw;
+                        else pool.chunks[cur].next = nw;
+                        cur = nw;
+                    }
+                    sm.slot_chunk[k] = cur;
+                }
+                sm.cur_chunk = cur;
+            }
+            __syncthreads();
+            int k = 0;
+            for (uint32_t m = tm; m; m &= m - 1, k++) {
+                const int j = __ffs(m) - 1;
+                const uint32_t e = n_tile + k;
+                WChunk& ck = pool.chunks[sm.slot_chunk[k]];
+                const int s = e & (kChunkEntries - 1);
+                ck.w[s][tid] = sm.wbuf[j][tid];
+                if (tid == 0) {
+                    uint32_t strips = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) strips |= ((sm.wmask[q] >> j) & 1u) << q;
+                    ck.meta[s] = make_uint2(sm.ids[j], strips);
+                }
+            }
+            n_tile += n_act;
+        }
+    }
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        if (DEPTH) out_depth[pix_id] = D;
+        atomicMax(&sm.s_last, last_contributor);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tile_last[tile] = sm.s_last;
+        pool.count[tile] = n_tile;
+        pool.tail[tile] = sm.cur_chunk;
+        if (n_tile == 0) pool.head[tile] = kNone;
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int CH, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
+    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
+    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
+    constexpr int MCH = CH / 8;
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;           // chunk index fastest: the CTAs of one tile are
+    const int ch0 = (blockIdx.x % nchunksC) * CH;     // co-scheduled and share its weight rows in L2
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+
+    float2 acc[8][MCH / 2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
+
+    const uint32_t n = pool.count[tile];
+    uint32_t c = pool.head[tile];
+    const int woff = warp * 32 + pg * 8;
+    const int foff = ch0 + cg * MCH;
+    for (uint32_t e = 0; e < n;) {
+        const WChunk* ck = pool.chunks + min(c, pool.capacity - 1);
+        const int m = (int)min((uint32_t)kChunkEntries, n - e);
+        for (int s = 0; s < m; s++) {
+            const uint2 meta = ck->meta[s];
+            if (!((meta.y >> warp) & 1u)) continue;
+            const float4* wp = reinterpret_cast<const float4*>(&ck->w[s][woff]);
+            const float4 w0 = wp[0], w1 = wp[1];
+            const float* fr = features + (size_t)meta.x * C + foff;
+            float2 f[MCH / 2];
+            if (VEC) {
+#pragma unroll
+                for (int q = 0; q < MCH / 4; q++) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cg * MCH + 4 * q < nch) t = __ldg(reinterpret_cast<const float4*>(fr) + q);
+                    f[2 * q] = make_float2(t.x, t.y);
+                    f[2 * q + 1] = make_float2(t.z, t.w);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < MCH / 2; k++) {
+                    f[k].x = (cg * MCH + 2 * k < nch) ? __ldg(fr + 2 * k) : 0.f;
+                    f[k].y = (cg * MCH + 2 * k + 1 < nch) ? __ldg(fr + 2 * k + 1) : 0.f;
+                }
+            }
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+            }
+        }
+        e += m;
+        c = ck->next;
+    }
+
+    // out = acc + T * bg (forward.cu:372-373)
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (row < (uint32_t)H) {
+        const size_t plane = (size_t)H * W;
+        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+        float Tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < MCH; k++) {
+            const int chl = cg * MCH + k;
+            if (chl >= nch) continue;
+            const float bgc = bg_color[ch0 + chl];
+            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
+            if (vec) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward, pipelined
+// Same decomposition as blend_forward_v3_kernel, but every warp keeps RD entries in flight through
+// a private shared-memory ring filled with cp.async (one 16-byte LDGSTS per lane: lanes 0-7 the
+// warp's 32 weights, lanes 8-23 the 64-channel feature slice).  The direct-load version above waits
+// an L2 round trip per entry (ncu: long_scoreboard 12.7 stalls per issue, 23 % issue utilisation);
+// the ring hides it without spending accumulator registers on double buffering.  Entries whose
+// strip bit is clear are skipped at issue time, so the consumer only sees Gaussians that touch it.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Walks one tile's chunk list front to back and yields the entries whose strip bit `bit` is set
+// (bit < 0: every entry).  Lane s < 16 keeps meta[s] of the current chunk in registers.
+struct EntryCursor {
+    const WChunk* chunks;
+    uint32_t capacity;
+    const WChunk* ck;
+    uint32_t n, e0, c, nextc, act;
+    uint2 mlane;
+    __device__ __forceinline__ void load_chunk(int lane, int bit) {
+        ck = chunks + min(c, capacity - 1);
+        const int m = (int)min((uint32_t)kChunkEntries, n - e0);
+        mlane = make_uint2(0u, 0u);
+        if (lane < m) mlane = ck->meta[lane];
+        const bool on = lane < m && (bit < 0 || ((mlane.y >> bit) & 1u));
+        act = __ballot_sync(0xffffffffu, on);
+        nextc = ck->next;
+    }
+    __device__ __forceinline__ void init(const PoolView& pool, int tile, int lane, int bit) {
+        chunks = pool.chunks;
+        capacity = pool.capacity;
+        n = pool.count[tile];
+        c = pool.head[tile];
+        e0 = 0;
+        act = 0;
+        if (n) load_chunk(lane, bit);
+    }
+    // slot index (0..15) of the next selected entry inside `ck`, or -1 when the list is exhausted
+    __device__ __forceinline__ int next(int lane, int bit) {
+        while (act == 0) {
+            if (n == 0 || e0 + kChunkEntries >= n) return -1;
+            e0 += kChunkEntries;
+            c = nextc;
+            load_chunk(lane, bit);
+        }
+        const int s = __ffs(act) - 1;
+        act &= act - 1;
+        return s;
+    }
+};
+
+template <int CH, int RD>
+__global__ void __launch_bounds__(kThreads, 2) blend_forward_v3r_kernel(
+    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
+    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
+    constexpr int MCH = CH / 8;
+    constexpr int ROW = 32 + CH;  // floats per ring slot: 32 weights + CH features
+    static_assert(ROW % 4 == 0 && ROW / 4 <= 32, "one 16-byte cp.async per lane");
+    __shared__ __align__(16) float ring[kThreads / 32][RD][ROW];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;
+    const int ch0 = (blockIdx.x % nchunksC) * CH;
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+
+    float2 acc[8][MCH / 2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
+
+    EntryCursor cur;
+    cur.init(pool, tile, lane, warp);
+    auto issue = [&](int slot) -> bool {  // always commits exactly one group
+        const int s = cur.next(lane, warp);
+        if (s >= 0) {
+            const uint32_t gid = __shfl_sync(0xffffffffu, cur.mlane.x, s);
+            if (lane < ROW / 4) {
+                const float* src;
+                int bytes = 16;
+                if (lane < 8) {
+                    src = &cur.ck->w[s][warp * 32 + lane * 4];
+                } else {
+                    const int k = (lane - 8) * 4;
+                    src = features + (size_t)gid * C + ch0 + k;
+                    if (k >= nch) { bytes = 0; src = features; }
+                }
+                cp_async16(&ring[warp][slot][lane * 4], src, bytes);
+            }
+        }
+        cp_async_commit();
+        return s >= 0;
+    };
+
+    int issued = 0, consumed = 0;
+    bool more = true;
+#pragma unroll
+    for (int i = 0; i < RD; i++) {
+        if (more) { more = issue(i); issued += more ? 1 : 0; }
+        else cp_async_commit();
+    }
+    while (consumed < issued) {
+        cp_async_wait<RD - 1>();
+        __syncwarp();
+        const int slot = consumed % RD;
+        const float* rs = ring[warp][slot];
+        const float4 w0 = *reinterpret_cast<const float4*>(rs + pg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(rs + pg * 8 + 4);
+        float2 f[MCH / 2];
+#pragma unroll
+        for (int q = 0; q < MCH / 4; q++) {
+            const float4 t = *reinterpret_cast<const float4*>(rs + 32 + cg * MCH + 4 * q);
+            f[2 * q] = make_float2(t.x, t.y);
+            f[2 * q + 1] = make_float2(t.z, t.w);
+        }
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+            for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+        }
+        consumed++;
+        __syncwarp();  // the slot is free again
+        if (more) { more = issue(slot); issued += more ? 1 : 0; }
+        else cp_async_commit();
+    }
+    cp_async_wait<0>();
+
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (row < (uint32_t)H) {
+        const size_t plane = (size_t)H * W;
+        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+        float Tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < MCH; k++) {
+            const int chl = cg * MCH + k;
+            if (chl >= nch) continue;
+            const float bgc = bg_color[ch0 + chl];
+            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
+            if (vec) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward 1
+// s = <feature, dL/dout> over ALL channels per (pixel, entry), then the back-to-front chain.
+constexpr int kSeg = 64;  // entries per segment (4 chunks); S[8 warps][kSeg][32 lanes] = 64 KB
+
+template <int CH, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) chain_backward_v3_kernel(
+    int W, int H, int C, const float* __restrict__ bg_color, const SplatRec* __restrict__ rec,
+    const float* __restrict__ features, const float* __restrict__ final_Ts, const float* __restrict__ dL_dpixels,
+    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity) {
+    constexpr int MCH = CH / 8;
+    static_assert(MCH == 8, "chain_backward_v3 uses 64-channel passes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*S)[kSeg][32] = reinterpret_cast<float(*)[kSeg][32]>(smem_raw);
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
+    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const uint32_t n = pool.count[tile];
+    if (n == 0) return;
+
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    const size_t plane = (size_t)H * W;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int woff = warp * 32 + lane;
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    float last_alpha = 0.f, s_last = 0.f, A = 0.f, bgdot = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    uint32_t remaining = n;
+    uint32_t cend = pool.tail[tile];
+    bool first = true;
+    while (remaining > 0) {
+        // segment = up to 4 chunks ending at cend (cidx[0] = last chunk of the segment)
+        uint32_t cidx[4] = {0, 0, 0, 0};
+        int cnts[4] = {0, 0, 0, 0};
+        int nck = 0, seg = 0;
+        {
+            uint32_t c = min(cend, pool.capacity - 1), r = remaining;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (r > 0) {
+                    const int m = (int)((r - 1) & (kChunkEntries - 1)) + 1;
+                    cidx[q] = c;
+                    cnts[q] = m;
+                    seg += m;
+                    r -= m;
+                    c = min(pool.chunks[c].prev, pool.capacity - 1);
+                    nck = q + 1;
+                }
+            }
+            cend = c;
+        }
+        for (int li = 0; li < seg; li++) S[warp][li][lane] = 0.f;
+
+        for (int cc = 0; cc < nchunksC; cc++) {
+            const int ch0 = cc * CH;
+            const int nch = min(CH, C - ch0);
+            float dLm[8][MCH];
+#pragma unroll
+            for (int k = 0; k < MCH; k++) {
+                const float* src = dL_dpixels + (size_t)(ch0 + cg * MCH + k) * plane + (size_t)W * row + col0;
+                const bool chok = (cg * MCH + k) < nch && row < (uint32_t)H;
+#pragma unroll
+                for (int i = 0; i < 8; i++) dLm[i][k] = (chok && col0 + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
+            }
+            if (first) {  // background term of the own pixel (backward.cu:527-529), all channels
+                float part[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) part[i] = 0.f;
+#pragma unroll
+                for (int k = 0; k < MCH; k++) {
+                    const float bgc = (cg * MCH + k) < nch ? bg_color[ch0 + cg * MCH + k] : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) part[i] += bgc * dLm[i][k];
+                }
+                xreduce_step<8>(part, lane, 4);
+                xreduce_step<4>(part, lane, 2);
+                xreduce_step<2>(part, lane, 1);
+                bgdot += part[0];
+            }
+            int li = 0;
+#pragma unroll
+            for (int q = 3; q >= 0; q--) {
+                if (q >= nck) continue;
+                const WChunk* ck = pool.chunks + cidx[q];
+                for (int s = 0; s < cnts[q]; s++, li++) {
+                    const uint2 meta = ck->meta[s];
+                    if (!((meta.y >> warp) & 1u)) continue;
+                    const float* fr = features + (size_t)meta.x * C + ch0 + cg * MCH;
+                    float f[MCH];
+                    if (VEC) {
+#pragma unroll
+                        for (int v = 0; v < MCH / 4; v++) {
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (cg * MCH + 4 * v < nch) t = __ldg(reinterpret_cast<const float4*>(fr) + v);
+                            f[4 * v] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < MCH; k++) f[k] = (cg * MCH + k < nch) ? __ldg(fr + k) : 0.f;
+                    }
+                    float part[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) part[i] = f[0] * dLm[i][0];
+#pragma unroll
+                    for (int k = 1; k < MCH; k++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) part[i] = fmaf(f[k], dLm[i][k], part[i]);
+                    xreduce_step<8>(part, lane, 4);
+                    xreduce_step<4>(part, lane, 2);
+                    xreduce_step<2>(part, lane, 1);
+                    S[warp][li][lane] += part[0];
+                }
+            }
+        }
+
+        // back-to-front chain over the segment (backward.cu:477-550 in dot-product form)
+        int li = seg - 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q >= nck) continue;
+            const WChunk* ck = pool.chunks + cidx[q];
+            for (int s = cnts[q] - 1; s >= 0; s--, li--) {
+                const uint2 meta = ck->meta[s];
+                if (!((meta.y >> warp) & 1u)) continue;
+                const float w = ck->w[s][woff];
+                const float sdot = S[warp][li][lane];
+                const float4* rp = reinterpret_cast<const float4*>(rec + meta.x);
+                const float4 a = __ldg(rp), con_o = __ldg(rp + 1);
+                float gv[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) gv[v] = 0.f;
+                if (w != 0.f) {  // this pixel blended this Gaussian in the forward pass
+                    const float2 d = {a.x - pixf.x, a.y - pixf.y};
+                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    const float G = exp(power);
+                    const float alpha = min(0.99f, con_o.w * G);
+                    T = T / (1.f - alpha);
+                    A = last_alpha * s_last + (1.f - last_alpha) * A;
+                    s_last = sdot;
+                    float dL_dalpha = (sdot - A) * T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                    const float dL_dG = con_o.w * dL_dalpha;
+                    const float gdx = G * d.x, gdy = G * d.y;
+                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                    gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    gv[1] = dL_dG * dG_ddely * ddely_dy;
+                    gv[2] = -0.5f * gdx * d.x * dL_dG;
+                    gv[3] = -0.5f * gdx * d.y * dL_dG;
+                    gv[4] = -0.5f * gdy * d.y * dL_dG;
+                    gv[5] = G * dL_dalpha;
+                }
+                xreduce_step<8>(gv, lane, 4);
+                xreduce_step<4>(gv, lane, 2);
+                xreduce_step<2>(gv, lane, 1);
+                float gq = gv[0];
+                gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+                gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+                if (lane < 6) {
+                    const size_t id = meta.x;
+                    float* dst = lane < 2 ? dL_dmean2D + id * 3 + lane
+                               : lane < 5 ? dL_dconic2D + id * 4 + (lane == 4 ? 3 : lane - 2)
+                                          : dL_dopacity + id;
+                    red_add_f32(dst, gq);
+                }
+            }
+        }
+        remaining -= (uint32_t)seg;
+        first = false;
+    }
+}
+
+// ------------------------------------------------------------------------------------ backward 2
+template <int CH>
+__global__ void __launch_bounds__(kThreads, 2) dfeature_v3_kernel(int W, int H, int C,
+                                                                 const float* __restrict__ dL_dpixels,
+                                                                 PoolView pool, float* __restrict__ dL_dcolors) {
+    constexpr int MCH = CH / 8;
+    static_assert(MCH == 8, "dfeature_v3 uses 8-channel slices per warp");
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;
+    const int ch0 = (blockIdx.x % nchunksC) * CH;
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = pool.count[tile];
+    if (n == 0 || warp * MCH >= nch) return;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    // lane <-> tile pixels [8*lane, 8*lane+8): row = lane>>1, columns (lane&1)*8 ..
+    const uint32_t row = pix_min.y + (lane >> 1);
+    const uint32_t col0 = pix_min.x + (lane & 1) * 8;
+    const size_t plane = (size_t)H * W;
+    float dLm[8][MCH];
+#pragma unroll
+    for (int k = 0; k < MCH; k++) {
+        const float* src = dL_dpixels + (size_t)(ch0 + warp * MCH + k) * plane + (size_t)W * row + col0;
+        const bool chok = (warp * MCH + k) < nch && row < (uint32_t)H;
+#pragma unroll
+        for (int i = 0; i < 8; i++) dLm[i][k] = (chok && col0 + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
+    }
+    uint32_t c = pool.head[tile];
+    for (uint32_t e = 0; e < n;) {
+        const WChunk* ck = pool.chunks + min(c, pool.capacity - 1);
+        const int m = (int)min((uint32_t)kChunkEntries, n - e);
+        for (int s = 0; s < m; s++) {
+            const uint2 meta = ck->meta[s];
+            const float4* wp = reinterpret_cast<const float4*>(&ck->w[s][lane * 8]);
+            const float4 w0 = wp[0], w1 = wp[1];
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float pdf[8];
+#pragma unroll
+            for (int k = 0; k < MCH; k++) {
+                pdf[k] = wv[0] * dLm[0][k];
+#pragma unroll
+                for (int i = 1; i < 8; i++) pdf[k] = fmaf(wv[i], dLm[i][k], pdf[k]);
+            }
+            xreduce_step<8>(pdf, lane, 4);
+            xreduce_step<4>(pdf, lane, 2);
+            xreduce_step<2>(pdf, lane, 1);
+            float v = pdf[0];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 8 && warp * MCH + lane < nch)
+                red_add_f32(dL_dcolors + (size_t)meta.x * C + ch0 + warp * MCH + lane, v);
+        }
+        e += m;
+        c = ck->next;
+    }
+}
+
+// ------------------------------------------------------------------------------------ GEMM-shaped kernels
+// With the weights materialised per tile, the three C-wide contractions are small dense GEMMs over the
+// tile's touching Gaussians (G ~ 115 on K3), done in fp32 on the CUDA cores (north_star: no tensor cores;
+// the 1e-4 fp32 bar rules out TF32 anyway):
+//     forward   out[256 px][64 ch]  = W^T[256 px][G]  . F[G][64 ch]      K = G      lane tile 8 px x 8 ch
+//     s-pass    S[256 px][G]        = dL[256 px][C]   . F^T[C][G]        K = C      lane tile 8 px x 8 entries
+//     dfeature  dF[G][64 ch]        = W[G][256 px]    . dL[256 px][64]   K = 256 px lane tile 4 entries x 8 ch
+// Register tiles make every product 64-128 FMAs per 4-6 shared/L1 loads and need no cross-lane
+// reductions (the shuffle-reduce variants above spend ~40 % of their issue slots on SHFL/FSEL/FADD).
+constexpr int kEB = 64;  // entries per staged batch
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Sequential reader of a tile's entry list for whole-CTA staging: thread t < cnt gets entry base+t.
+struct BatchCursor {
+    uint32_t n, done, c0;  // entries, entries already handed out, chunk holding entry `done`
+    __device__ __forceinline__ void init(const PoolView& pool, int tile) {
+        n = pool.count[tile];
+        done = 0;
+        c0 = pool.head[tile];
+    }
+};
+// chunk index holding entry (done + k): walks `next` pointers (k / 16 hops, at most 4)
+__device__ __forceinline__ uint32_t chunk_at(const PoolView& pool, uint32_t c0, int k) {
+    uint32_t c = min(c0, pool.capacity - 1);
+    for (int h = k / kChunkEntries; h > 0; h--) c = min(pool.chunks[c].next, pool.capacity - 1);
+    return c;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads, 2) blend_forward_gemm_kernel(
+    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
+    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
+    constexpr int MCH = CH / 8;
+    static_assert(CH == 64, "feature staging assumes 64-channel chunks");
+    __shared__ __align__(16) float Fs[2][kEB][CH];         // feature slices of the staged entries (2 x 16 KB)
+    __shared__ const float* Wrow[2][kEB];                  // weight row of each staged entry
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;
+    const int ch0 = (blockIdx.x % nchunksC) * CH;
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+
+    float2 acc[8][MCH / 2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
+
+    BatchCursor bc;
+    bc.init(pool, tile);
+    const int nb = (int)((bc.n + kEB - 1) / kEB);
+    // staging: thread t -> entry t>>2 of the batch, 16 channels (t&3)*16 .. +16 as 4 x cp.async(16 B)
+    auto stage = [&](int b, int buf) {
+        const int base = b * kEB;
+        const int cnt = min(kEB, (int)bc.n - base);
+        const int e = tid >> 2, q = tid & 3;
+        if (e < cnt) {
+            const uint32_t c = chunk_at(pool, bc.c0, e);
+            const WChunk* ck = pool.chunks + c;
+            const int s = (base + e) & (kChunkEntries - 1);
+            const uint32_t gid = ck->meta[s].x;
+            if (q == 0) Wrow[buf][e] = &ck->w[s][0];
+            const float* src = features + (size_t)gid * C + ch0 + q * 16;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int k = q * 16 + v * 4;
+                cp_async16(&Fs[buf][e][k], k < nch ? src + v * 4 : features, k < nch ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+    if (nb > 0) stage(0, 0);
+    for (int b = 0; b < nb; b++) {
+        const int buf = b & 1;
+        const int cnt = min(kEB, (int)bc.n - b * kEB);
+        cp_async_wait<0>();
+        __syncthreads();  // batch b staged by everyone; batch b-1 fully consumed
+        if (b + 1 < nb) {
+            // advance the cursor to the first chunk of batch b+1 (kEB / 16 hops), uniformly
+            uint32_t c = min(bc.c0, pool.capacity - 1);
+#pragma unroll
+            for (int h = 0; h < kEB / kChunkEntries; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
+            bc.c0 = c;
+            stage(b + 1, buf ^ 1);
+        }
+        const int woff = warp * 32 + pg * 8;
+        constexpr int PF = 12;  // weight-row prefetch distance (entries); rows are L2/DRAM resident
+        if ((lane & 7) == 0)
+            for (int e = 0; e < min(PF, cnt); e++) prefetch_l1(Wrow[buf][e] + woff);
+#pragma unroll 4
+        for (int e = 0; e < cnt; e++) {
+            if ((lane & 7) == 0 && e + PF < cnt) prefetch_l1(Wrow[buf][e + PF] + woff);
+            const float4* wp = reinterpret_cast<const float4*>(Wrow[buf][e] + woff);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            float2 f[MCH / 2];
+#pragma unroll
+            for (int q = 0; q < MCH / 4; q++) {
+                const float4 t = *reinterpret_cast<const float4*>(&Fs[buf][e][cg * MCH + 4 * q]);
+                f[2 * q] = make_float2(t.x, t.y);
+                f[2 * q + 1] = make_float2(t.z, t.w);
+            }
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+            }
+        }
+    }
+
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (row < (uint32_t)H) {
+        const size_t plane = (size_t)H * W;
+        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+        float Tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < MCH; k++) {
+            const int chl = cg * MCH + k;
+            if (chl >= nch) continue;
+            const float bgc = bg_color[ch0 + chl];
+            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
+            if (vec) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
+            }
+        }
+    }
+}
+
+// Forward GEMM with a TMA-fed ring.  ncu on blend_forward_gemm_kernel: 67 % of the instructions are
+// packed FMAs but only 28 % of the issue slots are used — every warp waits an L2/DRAM round trip on
+// its weight loads (long_scoreboard 9.2 stalls per issue).  Here each staged Gaussian is two 1-D bulk
+// copies (cp.async.bulk: the 1 KB weight row and the 256 B feature slice) into a ring of NS stages
+// of ES entries guarded by full/empty mbarriers; warp 0 issues stage b+NS-1 after consuming stage b,
+// so up to (NS-1)*ES entries are in flight and no warp ever blocks on a global load.
+template <int CH, int ES, int NS>
+__global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
+    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
+    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
+    constexpr int MCH = CH / 8;
+    static_assert(ES <= 32, "one lane of warp 0 per staged entry");
+    struct Stage {
+        float w[ES][SGB_TILE_PIX];
+        float f[ES][CH];
+    };
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage* stg = reinterpret_cast<Stage*>(smem_raw);
+    __shared__ uint64_t full_bar[NS], empty_bar[NS];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;
+    const int ch0 = (blockIdx.x % nchunksC) * CH;
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+
+    const uint32_t n = pool.count[tile];
+    const int nb = (int)((n + ES - 1) / ES);
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    if (nch < CH)  // zero the never-written tail of every feature row once
+        for (int e = tid; e < NS * ES * CH; e += kThreads) {
+            const int k = e % CH;
+            if (k >= nch) stg[e / (ES * CH)].f[(e / CH) % ES][k] = 0.f;
+        }
+    __syncthreads();
+
+    // producer state (warp 0): chunk holding the first entry of the next batch to issue
+    uint32_t pc = pool.head[tile];
+    int pb = 0;  // next batch to issue
+    auto produce = [&]() {  // warp 0, converged
+        const int st = pb % NS;
+        const int base = pb * ES;
+        const int cnt = min(ES, (int)n - base);
+        if (pb >= NS) mbar_wait(&empty_bar[st], (uint32_t)(((pb / NS) - 1) & 1));  // all 8 warps released it
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], (uint32_t)cnt * (SGB_TILE_PIX * 4u + (uint32_t)nch * 4u));
+        if (lane < cnt) {
+            const uint32_t c = chunk_at(pool, pc, lane);
+            const WChunk* ck = pool.chunks + c;
+            const int s = (base + lane) & (kChunkEntries - 1);
+            const uint32_t gid = ck->meta[s].x;
+            bulk_g2s(&stg[st].w[lane][0], &ck->w[s][0], SGB_TILE_PIX * 4u, &full_bar[st]);
+            bulk_g2s(&stg[st].f[lane][0], features + (size_t)gid * C + ch0, (uint32_t)nch * 4u, &full_bar[st]);
+        }
+        // advance to the chunk holding entry base + ES
+        const int hops = ((base & (kChunkEntries - 1)) + ES) / kChunkEntries;
+        uint32_t c = min(pc, pool.capacity - 1);
+        for (int h = 0; h < hops; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
+        pc = c;
+        pb++;
+    };
+    if (warp == 0)
+        for (int i = 0; i < NS - 1 && pb < nb; i++) produce();
+
+    float2 acc[8][MCH / 2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
+
+    const int woff = warp * 32 + pg * 8;
+    for (int b = 0; b < nb; b++) {
+        const int st = b % NS;
+        const int cnt = min(ES, (int)n - b * ES);
+        if (warp == 0 && pb < nb) produce();  // refill the stage everybody left one batch ago
+        mbar_wait(&full_bar[st], (uint32_t)((b / NS) & 1));
+#pragma unroll 4
+        for (int e = 0; e < cnt; e++) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&stg[st].w[e][woff]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&stg[st].w[e][woff + 4]);
+            float2 f[MCH / 2];
+#pragma unroll
+            for (int q = 0; q < MCH / 4; q++) {
+                const float4 t = *reinterpret_cast<const float4*>(&stg[st].f[e][cg * MCH + 4 * q]);
+                f[2 * q] = make_float2(t.x, t.y);
+                f[2 * q + 1] = make_float2(t.z, t.w);
+            }
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (row < (uint32_t)H) {
+        const size_t plane = (size_t)H * W;
+        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+        float Tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < MCH; k++) {
+            const int chl = cg * MCH + k;
+            if (chl >= nch) continue;
+            const float bgc = bg_color[ch0 + chl];
+            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
+            if (vec) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
+            }
+        }
+    }
+}
+
+// dF[entry][ch] = sum over the tile's 256 pixels of w[entry][px] * dL/dout[px][ch].
+// CTA = (tile, 64-channel chunk); the dL tile sits in shared memory as [px][ch]; warp w owns entries
+// 16w .. 16w+15 of each 128-entry pass; lane = (eg, cg) holds a 4-entry x 8-channel accumulator tile.
+template <int CH>
+__global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H, int C,
+                                                                   const float* __restrict__ dL_dpixels,
+                                                                   PoolView pool, float* __restrict__ dL_dcolors) {
+    static_assert(CH == 64, "64-channel chunks");
+    constexpr int PITCH = CH + 4;  // floats per pixel row of the smem dL tile (keeps 16-byte alignment)
+    constexpr int WP = 36;         // pitch of the per-warp weight slab rows (32 px + pad)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*dLs)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem_raw);
+    float* wslab = reinterpret_cast<float*>(smem_raw + sizeof(float) * SGB_TILE_PIX * PITCH);
+    __shared__ const float* Wrow[128];
+    __shared__ uint32_t Gid[128];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nchunksC = (C + CH - 1) / CH;
+    const int tile = blockIdx.x / nchunksC;
+    const int ch0 = (blockIdx.x % nchunksC) * CH;
+    const int nch = min(CH, C - ch0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = pool.count[tile];
+    if (n == 0) return;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    const size_t plane = (size_t)H * W;
+    // dL tile -> smem [px][ch]: a thread reads the 16 pixels of one tile row of one channel (64 B);
+    // lanes take consecutive channels so the transposing stores are bank-conflict free
+    for (int idx = tid; idx < CH * SGB_TILE; idx += kThreads) {
+        const int c = idx % CH, r = idx / CH;
+        const uint32_t y = pix_min.y + r;
+        const bool ok = c < nch && y < (uint32_t)H;
+        const float* src = dL_dpixels + (size_t)(ch0 + c) * plane + (size_t)W * y + pix_min.x;
+#pragma unroll
+        for (int x = 0; x < SGB_TILE; x++)
+            dLs[r * SGB_TILE + x][c] = (ok && pix_min.x + x < (uint32_t)W) ? __ldg(src + x) : 0.f;
+    }
+    const int eg = lane >> 3, cg = lane & 7;
+    uint32_t c0 = pool.head[tile];
+    for (uint32_t base = 0; base < n; base += 128) {
+        const int cnt = (int)min(128u, n - base);
+        __syncthreads();  // dLs ready (first pass) / previous pass done with Wrow, Gid
+        if (tid < cnt) {
+            const uint32_t c = chunk_at(pool, c0, tid);
+            const WChunk* ck = pool.chunks + c;
+            const int s = (base + tid) & (kChunkEntries - 1);
+            Wrow[tid] = &ck->w[s][0];
+            Gid[tid] = ck->meta[s].x;
+        }
+        __syncthreads();
+        const int e0 = warp * 16 + eg * 4;  // this lane's 4 entries
+        if (warp * 16 < cnt) {
+            // Weight rows stream through a private double-buffered slab [16 entries][32 px] filled with
+            // cp.async (4 x 16 B per lane per slab): the direct-load version waited a DRAM/L2 round trip
+            // on every K step (ncu: long_scoreboard 10 stalls per issue, 18 % issue utilisation).
+            float(*wsl)[16][WP] = reinterpret_cast<float(*)[16][WP]>(wslab + (size_t)warp * 2 * 16 * WP);
+            const float* lrow[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) lrow[i] = Wrow[min(warp * 16 + (lane >> 3) + 4 * i, cnt - 1)] + (lane & 7) * 4;
+            auto issue = [&](int sl, int buf) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    cp_async16(&wsl[buf][(lane >> 3) + 4 * i][(lane & 7) * 4], lrow[i] + sl * 32, 16);
+                cp_async_commit();
+            };
+            float2 acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[j][k] = make_float2(0.f, 0.f);
+            issue(0, 0);
+            for (int sl = 0; sl < SGB_TILE_PIX / 32; sl++) {
+                const int buf = sl & 1;
+                if (sl + 1 < SGB_TILE_PIX / 32) { issue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncwarp();
+#pragma unroll 2
+                for (int p4 = 0; p4 < 8; p4++) {
+                    float4 wq[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wq[j] = *reinterpret_cast<const float4*>(&wsl[buf][eg * 4 + j][p4 * 4]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int px = sl * 32 + p4 * 4 + u;
+                        const float4 d0 = *reinterpret_cast<const float4*>(&dLs[px][cg * 8]);
+                        const float4 d1 = *reinterpret_cast<const float4*>(&dLs[px][cg * 8 + 4]);
+                        const float2 dd[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y),
+                                              make_float2(d1.z, d1.w)};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float wj = u == 0 ? wq[j].x : u == 1 ? wq[j].y : u == 2 ? wq[j].z : wq[j].w;
+                            const float2 w2 = make_float2(wj, wj);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) acc[j][k] = ffma2(dd[k], w2, acc[j][k]);
+                        }
+                    }
+                }
+                __syncwarp();  // slab `buf` may be refilled by the next issue
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (e0 + j < cnt && cg * 8 < nch) {
+                    float* dst = dL_dcolors + (size_t)Gid[e0 + j] * C + ch0 + cg * 8;
+                    if (cg * 8 + 8 <= nch && (C & 3) == 0) {
+                        red_add_v4_f32(dst, make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y));
+                        red_add_v4_f32(dst + 4, make_float4(acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y));
+                    } else {
+                        const float v[8] = {acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y,
+                                            acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y};
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (cg * 8 + k < nch) red_add_f32(dst + k, v[k]);
+                    }
+                }
+            }
+        }
+        // first chunk of the next pass: 128 / 16 hops
+        uint32_t c = min(c0, pool.capacity - 1);
+        for (int h = 0; h < 128 / kChunkEntries && base + 128 < n; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
+        c0 = c;
+    }
+}
+
+// Backward chain with the s-pass as a GEMM over channels.  CTA = tile; segments of 64 entries walked
+// from the back of the list; per segment S[32 px][64 entries] per warp accumulates in registers over
+// all channels (lane tile 8 px x 8 entries), is parked in shared memory, and lane = pixel then runs
+// the reference's back-to-front chain over the segment.
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
+    int W, int H, int C, const float* __restrict__ bg_color, const SplatRec* __restrict__ rec,
+    const float* __restrict__ features, const float* __restrict__ final_Ts, const float* __restrict__ dL_dpixels,
+    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity) {
+    constexpr int CK = 16;         // channels per staged slab
+    constexpr int FP = kSeg + 4;   // pitch of the transposed feature slab [ch][entry]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*S)[kSeg][32] = reinterpret_cast<float(*)[kSeg][32]>(smem_raw);                       // 64 KB
+    float(*FT)[CK][FP] = reinterpret_cast<float(*)[CK][FP]>(smem_raw + sizeof(float) * 8 * kSeg * 32);  // 2 slabs
+    float(*DS)[2][CK][32] = reinterpret_cast<float(*)[2][CK][32]>(
+        smem_raw + sizeof(float) * (8 * kSeg * 32 + 2 * CK * FP));  // per-warp dL slabs, 2 x 2 KB each
+    __shared__ const float* Wrow[kSeg];
+    __shared__ uint2 Meta[kSeg];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, eg = lane & 7;
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
+    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const uint32_t n = pool.count[tile];
+    if (n == 0) return;
+
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    const size_t plane = (size_t)H * W;
+    const bool rowok = row < (uint32_t)H;
+    const bool vec8 = rowok && ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+    const int woff = warp * 32 + lane;
+
+    // background term of the own pixel over all channels (backward.cu:527-529)
+    float bgdot = 0.f;
+    if (inside)
+        for (int ch = 0; ch < C; ch++) bgdot += bg_color[ch] * __ldg(dL_dpixels + (size_t)ch * plane + pix_id);
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    float last_alpha = 0.f, s_last = 0.f, A = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    // segments are aligned to 64 entries from the FRONT so that a segment is exactly 4 whole chunks
+    // (the last one may be partial); they are visited back to front.
+    const int nseg = (int)((n + kSeg - 1) / kSeg);
+    for (int sg = nseg - 1; sg >= 0; sg--) {
+        const int base = sg * kSeg;
+        const int cnt = min(kSeg, (int)n - base);
+        __syncthreads();  // previous segment done with S / Wrow / Meta / FT
+        if (tid < kSeg) {
+            if (tid < cnt) {
+                uint32_t c = min(pool.head[tile], pool.capacity - 1);
+                for (int h = (base + tid) / kChunkEntries; h > 0; h--) c = min(pool.chunks[c].next, pool.capacity - 1);
+                const WChunk* ck = pool.chunks + c;
+                const int s = (base + tid) & (kChunkEntries - 1);
+                Wrow[tid] = &ck->w[s][0];
+                Meta[tid] = ck->meta[s];
+            } else {
+                Meta[tid] = make_uint2(0u, 0u);
+            }
+        }
+        __syncthreads();
+
+        float2 acc[8][4];  // [px][entry pair]
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+
+        const int nslab = (C + CK - 1) / CK;
+        // feature slab: thread t -> entry t>>2, 4 channels (t&3)*4.. of the slab; loaded into registers
+        // one slab ahead, stored transposed [ch][entry] after the current slab's math
+        float4 fpre;
+        auto fload = [&](int sl) {
+            const int e = tid >> 2, q = tid & 3;
+            const int chb = sl * CK + q * 4;
+            fpre = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < cnt) {
+                const float* src = features + (size_t)Meta[e].x * C + chb;
+                if (VEC && chb + 4 <= C) fpre = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    if (chb < C) fpre.x = __ldg(src);
+                    if (chb + 1 < C) fpre.y = __ldg(src + 1);
+                    if (chb + 2 < C) fpre.z = __ldg(src + 2);
+                    if (chb + 3 < C) fpre.w = __ldg(src + 3);
+                }
+            }
+        };
+        auto fstore = [&](int buf) {
+            const int e = tid >> 2, q = tid & 3;
+            FT[buf][q * 4 + 0][e] = fpre.x;
+            FT[buf][q * 4 + 1][e] = fpre.y;
+            FT[buf][q * 4 + 2][e] = fpre.z;
+            FT[buf][q * 4 + 3][e] = fpre.w;
+        };
+        // dL slab [CK ch][32 px of this warp]: 4 x cp.async(16 B) per lane, private to the warp
+        auto dissue = [&](int sl, int buf) {
+#pragma unroll
+            for (int i = 0; i < CK / 4; i++) {
+                const int chl = (lane >> 3) + 4 * i;
+                const int ch = sl * CK + chl;
+                const int pc = lane & 7;  // 16-byte piece: tile row pc>>2 of the strip, columns (pc&3)*4..
+                const uint32_t y = pix_min.y + 2 * warp + (pc >> 2);
+                const uint32_t x = pix_min.x + (pc & 3) * 4;
+                const bool ok = ch < C && y < (uint32_t)H && x + 4 <= (uint32_t)W;
+                const float* src = ok ? dL_dpixels + (size_t)ch * plane + (size_t)W * y + x : dL_dpixels;
+                cp_async16(&DS[warp][buf][chl][pc * 4], src, ok ? 16 : 0);
+            }
+            cp_async_commit();
+        };
+        fload(0);
+        dissue(0, 0);
+        fstore(0);
+        if (nslab > 1) fload(1);
+        for (int sl = 0; sl < nslab; sl++) {
+            const int buf = sl & 1;
+            if (sl + 1 < nslab) { dissue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();  // FT[buf] stored by everyone, this warp's dL slab landed; slab sl-1 consumed
+#pragma unroll 4
+            for (int k = 0; k < CK; k++) {
+                const float4 d0 = *reinterpret_cast<const float4*>(&DS[warp][buf][k][pg * 8]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&DS[warp][buf][k][pg * 8 + 4]);
+                const float4 f0 = *reinterpret_cast<const float4*>(&FT[buf][k][eg * 8]);
+                const float4 f1 = *reinterpret_cast<const float4*>(&FT[buf][k][eg * 8 + 4]);
+                const float2 ff[4] = {make_float2(f0.x, f0.y), make_float2(f0.z, f0.w), make_float2(f1.x, f1.y),
+                                      make_float2(f1.z, f1.w)};
+                const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float2 d2 = make_float2(d[i], d[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = ffma2(ff[j], d2, acc[i][j]);
+                }
+            }
+            if (sl + 1 < nslab) {
+                fstore(buf ^ 1);  // readers of FT[buf^1] (slab sl-1) all passed this iteration's barrier
+                if (sl + 2 < nslab) fload(sl + 2);
+            }
+            __syncwarp();  // every lane is done with DS[warp][buf] before the next cp.async refills it
+        }
+        // park S: S[warp][entry][px]
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float* dst = &S[warp][eg * 8 + j][pg * 8];
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncwarp();
+
+        // back-to-front chain over the segment (backward.cu:477-550 in dot-product form)
+        for (int li = cnt - 1; li >= 0; li--) {
+            const uint2 meta = Meta[li];
+            if (!((meta.y >> warp) & 1u)) continue;
+            const float w = __ldg(Wrow[li] + woff);
+            const float sdot = S[warp][li][lane];
+            const float4* rp = reinterpret_cast<const float4*>(rec + meta.x);
+            const float4 a = __ldg(rp), con_o = __ldg(rp + 1);
+            float gv[8];
+#pragma unroll
+            for (int v = 0; v < 8; v++) gv[v] = 0.f;
+            if (w != 0.f) {
+                const float2 d = {a.x - pixf.x, a.y - pixf.y};
+                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                const float G = exp(power);
+                const float alpha = min(0.99f, con_o.w * G);
+                T = T / (1.f - alpha);
+                A = last_alpha * s_last + (1.f - last_alpha) * A;
+                s_last = sdot;
+                float dL_dalpha = (sdot - A) * T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                const float dL_dG = con_o.w * dL_dalpha;
+                const float gdx = G * d.x, gdy = G * d.y;
+                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                gv[1] = dL_dG * dG_ddely * ddely_dy;
+                gv[2] = -0.5f * gdx * d.x * dL_dG;
+                gv[3] = -0.5f * gdx * d.y * dL_dG;
+                gv[4] = -0.5f * gdy * d.y * dL_dG;
+                gv[5] = G * dL_dalpha;
+            }
+            xreduce_step<8>(gv, lane, 4);
+            xreduce_step<4>(gv, lane, 2);
+            xreduce_step<2>(gv, lane, 1);
+            float gq = gv[0];
+            gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+            gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+            if (lane < 6) {
+                const size_t id = meta.x;
+                float* dst = lane < 2 ? dL_dmean2D + id * 3 + lane
+                           : lane < 5 ? dL_dconic2D + id * 4 + (lane == 4 ? 3 : lane - 2)
+                                      : dL_dopacity + id;
+                red_add_f32(dst, gq);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+size_t pool_bytes(int tiles, uint32_t chunks, PoolView* v, void* base) {
+    size_t off = 0;
+    char* p = (char*)base;
+    auto take = [&](size_t n) { size_t o = off; off += align_up(n); return p ? p + o : nullptr; };
+    void* hdr = take(sizeof(PoolHdr));
+    void* head = take(4 * (size_t)tiles);
+    void* tail = take(4 * (size_t)tiles);
+    void* cnt = take(4 * (size_t)tiles);
+    void* ch = take(sizeof(WChunk) * (size_t)chunks);
+    if (v) {
+        v->hdr = (PoolHdr*)hdr; v->head = (uint32_t*)head; v->tail = (uint32_t*)tail; v->count = (uint32_t*)cnt;
+        v->chunks = (WChunk*)ch; v->capacity = chunks;
+    }
+    return off;
+}
+
+}  // namespace
+
+// Runs the alpha pass into the ctx pool, growing the pool and retrying when it was too small.
+// Synchronises the stream (4-byte read-back of the overflow flag).
+static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                          float* out_depth, PoolView* pv, cudaStream_t s) {
+    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    // first guess: ~8 chunks (128 touching Gaussians) per tile, bounded by the instance count
+    uint64_t guess = (uint64_t)tiles * 8;
+    const uint64_t by_R = (uint64_t)(R / kChunkEntries) + (uint64_t)tiles;
+    if (guess > by_R) guess = by_R;
+    if (guess < ctx->pool_chunks_hint) guess = ctx->pool_chunks_hint;
+    if (guess < 16) guess = 16;
+    const size_t smem = sizeof(AlphaSmem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const uint32_t chunks = (uint32_t)guess;
+        int rc = ctx->pool.ensure(pool_bytes(tiles, chunks, nullptr, nullptr));
+        if (rc) return rc;
+        pool_bytes(tiles, chunks, pv, ctx->pool.p);
+        SGB_CUDA(cudaMemsetAsync(pv->hdr, 0, sizeof(PoolHdr), s));
+        {
+            StageTimer t(ctx, ST_ALPHA, s);
+            if (out_depth)
+                alpha_pass_kernel<true><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec, im.final_T,
+                                                                    im.n_contrib, im.tile_last, out_depth, *pv);
+            else
+                alpha_pass_kernel<false><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec,
+                                                                     im.final_T, im.n_contrib, im.tile_last, nullptr, *pv);
+            SGB_LAUNCH_CHECK("alpha_pass_kernel", in.debug, s);
+            ctx->launches += 1;
+        }
+        uint32_t* h = (uint32_t*)ctx->pinned + 4;
+        SGB_CUDA(cudaMemcpyAsync(h, pv->hdr, sizeof(PoolHdr), cudaMemcpyDeviceToHost, s));
+        SGB_CUDA(cudaStreamSynchronize(s));
+        const uint32_t used = h[0], overflow = h[1];
+        if (!overflow) {
+            if (used > ctx->pool_chunks_hint) ctx->pool_chunks_hint = used + used / 16 + 16;
+            return SGB_OK;
+        }
+        guess = (uint64_t)used + used / 8 + 64;  // the counter kept counting: this is the real demand
+    }
+    set_error("weight pool kept overflowing");
+    return SGB_E_NOMEM;
+}
+
+int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                     const float* colors, float* out_color, cudaStream_t s) {
+    PoolView pv;
+    int rc = run_alpha_pass(ctx, in, R, g, b, im, nullptr, &pv, s);
+    if (rc) return rc;
+    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    const int chunks = (in.C + 63) / 64;
+    const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
+    StageTimer t(ctx, ST_BLEND_FWD, s);
+    ctx->launches += 1;
+    const char* dbg = getenv("SGB_FWD_DIRECT");  // diagnostics: 1 = direct loads, 2 = per-warp cp.async ring
+    if (vec && !dbg) {
+        constexpr int ES = 8, NS = 8;
+        const size_t smem_f = (size_t)NS * ES * (SGB_TILE_PIX + 64) * sizeof(float);
+        static bool fattr = false;
+        if (!fattr) {
+            SGB_CUDA(cudaFuncSetAttribute(blend_forward_tma_kernel<64, ES, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_f));
+            fattr = true;
+        }
+        blend_forward_tma_kernel<64, ES, NS><<<tiles * chunks, kThreads, smem_f, s>>>(in.W, in.H, in.C, colors,
+                                                                                      in.background, im.final_T, pv,
+                                                                                      out_color);
+    } else if (vec && dbg[0] == '3')
+        blend_forward_gemm_kernel<64><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
+                                                                          im.final_T, pv, out_color);
+    else if (vec && dbg[0] == '2')
+        blend_forward_v3r_kernel<64, 8><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
+                                                                            im.final_T, pv, out_color);
+    else if (vec)
+        blend_forward_v3_kernel<64, true><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
+                                                                                  im.final_T, pv, out_color);
+    else
+        blend_forward_v3_kernel<64, false><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
+                                                                                   im.final_T, pv, out_color);
+    SGB_LAUNCH_CHECK("blend_forward_v3_kernel", in.debug, s);
+    return SGB_OK;
+}
+
+int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                      const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                      float* dL_dopacity, float* dL_dcolors, cudaStream_t s) {
+    PoolView pv;
+    // the weight rows are scratch, not saved state: rebuild them (one chain pass, ~the cost of a 3-channel render)
+    int rc = run_alpha_pass(ctx, in, R, g, b, im, nullptr, &pv, s);
+    if (rc) return rc;
+    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    const int chunks = (in.C + 63) / 64;
+    const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
+    const size_t smem = sizeof(float) * 8 * kSeg * 32;
+    const size_t smem_g = smem + sizeof(float) * (2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
+    const size_t smem_d = sizeof(float) * (SGB_TILE_PIX * (64 + 4) + 8 * 2 * 16 * 36);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_v3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_v3_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+        attr_set = true;
+    }
+    const char* dbg = getenv("SGB_BWD_DIRECT");  // diagnostics: 1 = shuffle-reduce kernels instead of the GEMM-shaped ones
+    const bool rows16 = (in.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dL_dpix) & 15) == 0);
+    if (!dbg && rows16) {
+        {
+            StageTimer t(ctx, ST_BLEND_BWD, s);
+            ctx->launches += 1;
+            if (vec)
+                chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                                im.final_T, dL_dpix, pv, dL_dmean2D,
+                                                                                dL_dconic, dL_dopacity);
+            else
+                chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                                 im.final_T, dL_dpix, pv, dL_dmean2D,
+                                                                                 dL_dconic, dL_dopacity);
+            SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
+        }
+        StageTimer t(ctx, ST_DFEATURE, s);
+        ctx->launches += 1;
+        dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
+        SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
+        return SGB_OK;
+    }
+    {
+        StageTimer t(ctx, ST_BLEND_BWD, s);
+        ctx->launches += 1;
+        if (vec)
+            chain_backward_v3_kernel<64, true><<<tiles, kThreads, smem, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                            im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
+                                                                            dL_dopacity);
+        else
+            chain_backward_v3_kernel<64, false><<<tiles, kThreads, smem, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                             im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
+                                                                             dL_dopacity);
+        SGB_LAUNCH_CHECK("chain_backward_v3_kernel", in.debug, s);
+    }
+    {
+        StageTimer t(ctx, ST_DFEATURE, s);
+        ctx->launches += 1;
+        dfeature_v3_kernel<64><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
+        SGB_LAUNCH_CHECK("dfeature_v3_kernel", in.debug, s);
+    }
+    return SGB_OK;
+}
+
+}  // namespace sgb

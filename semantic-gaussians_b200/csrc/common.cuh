@@ -106,7 +106,8 @@ namespace sgb {
 // caller's stream; sgb_profile_read() sums the pairs recorded since the last read.
 enum Stage {
     ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
-    ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_TRANSPOSE, ST_FUSION_GATHER, ST_COUNT
+    ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_TRANSPOSE, ST_FUSION_GATHER, ST_ALPHA, ST_DFEATURE,
+    ST_COUNT
 };
 constexpr int kProfRing = 128;
 struct Profiler {
@@ -125,6 +126,8 @@ struct sgb_ctx {
     sgb::Scratch geom;     // depth-sort keys/values, offsets, CUB temp
     sgb::Scratch bin;      // unsorted / sorted tile keys, unsorted values, CUB temp
     sgb::Scratch misc;     // fusion: transposed feature map, z-buffer
+    sgb::Scratch pool;     // per-tile weight rows of the C-channel blend (blend_v3.cu)
+    uint64_t pool_chunks_hint = 0;  // high-water mark of the pool demand (chunks)
     int64_t* pinned = nullptr;  // host-pinned readback slot(s)
     // cached layout of the last sgb_forward_geometry call (consumed by sgb_forward_render)
     int64_t last_P = 0;
@@ -160,6 +163,11 @@ int launch_blend_forward(const sgb_view_inputs& in, GeomView g, BinView b, ImgVi
 int launch_blend_backward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                           const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, cudaStream_t s);
+int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                     const float* colors, float* out_color, cudaStream_t s);
+int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                      const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                      float* dL_dopacity, float* dL_dcolors, cudaStream_t s);
 int launch_geom_backward(const sgb_view_inputs& in, GeomView g, const int32_t* radii, const float* cov3D,
                          const float* dL_dcolor_rgb, const sgb_view_grads& gr, cudaStream_t s);
 
@@ -178,16 +186,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Waits for the phase with the given parity.  try_wait sleeps in hardware between polls; a bounded
+// spin turns a protocol bug into a trap (launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
 }
 // 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); dst/src 16-B aligned,
 // bytes a multiple of 16; completion is signalled on `bar` as transaction bytes.
