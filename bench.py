@@ -172,11 +172,14 @@ def run_cpu_reference(args, rank, world):
 def algorithmic_bytes(P, P_vis, R, C, W, H):
     """SURVEY.md §8(d) / BASELINE.md §4 compulsory traffic, split by kernel."""
     px = W * H
-    fwd_blend = 4 * C * P_vis + 4 * C * px + 8 * px + 4 * R + 32 * P_vis
-    bwd_blend = 4 * C * px + 8 * C * P_vis + 4 * R + 8 * px + 32 * P_vis + 28 * P_vis
+    # per kernel: every input read once, every output written once
+    alpha = 4 * R + 32 * P_vis + 8 * px                       # ids + splat records in, final_T / n_contrib out
+    fwd_blend = 4 * C * P_vis + 4 * C * px + 4 * px           # features in, image out (+ final_T in)
+    chain = 4 * C * px + 4 * C * P_vis + 32 * P_vis + 4 * px + 28 * P_vis   # dL/dout + features in, 7 geometry grads out
+    dfeat = 4 * C * px + 4 * C * P_vis                        # dL/dout in, dL/dfeature out
     fwd_total = 44 * P + 4 * C * P_vis + 4 * C * px + 8 * px + 24 * R
     bwd_total = 4 * C * px + 8 * C * P_vis + 4 * R + 8 * px + 80 * P + 44 * P
-    return dict(blend_fwd=fwd_blend, blend_bwd=bwd_blend, fwd=fwd_total, bwd=bwd_total)
+    return dict(alpha_pass=alpha, blend_fwd=fwd_blend, blend_bwd=chain, dfeature=dfeat, fwd=fwd_total, bwd=bwd_total)
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -340,7 +343,7 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     ab = algorithmic_bytes(P_GAUSS, P_vis, Rn, CHANNELS, WIDTH, HEIGHT)
     per_stage = {k: (v[0] / max(v[1], 1)) for k, v in stages.items() if v[1] > 0}
-    dom = max(("blend_fwd", "blend_bwd"), key=lambda k: per_stage.get(k, 0.0))
+    dom = max(("blend_fwd", "blend_bwd", "dfeature", "alpha_pass"), key=lambda k: per_stage.get(k, 0.0))
     dom_ms = per_stage.get(dom, float("nan"))
     achieved = ab[dom] / (dom_ms * 1e-3) * 1e-9
     traffic = None

@@ -161,6 +161,7 @@ int sgb_forward_geometry(sgb_ctx* ctx, const sgb_view_inputs* in, void* geometry
     }
     *num_rendered_host = 0;
     ctx->last_P = 0;
+    ctx->pool_valid = false;  // a new view starts: cached weight rows belong to the previous one
     if (in->P == 0) return SGB_OK;  // rasterize_points.cu:84: nothing to do for an empty scene
     GeomView g = GeomView::carve(geometry_state, in->P);
     rc = run_depth_order_and_scan(ctx, *in, g, radii, num_rendered_host, s);

@@ -996,19 +996,24 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
     }
 }
 
-// dF[entry][ch] = sum over the tile's 256 pixels of w[entry][px] * dL/dout[px][ch].
-// CTA = (tile, 64-channel chunk); the dL tile sits in shared memory as [px][ch]; warp w owns entries
-// 16w .. 16w+15 of each 128-entry pass; lane = (eg, cg) holds a 4-entry x 8-channel accumulator tile.
+// dF[entry][ch] = sum over the tile's 256 pixels of w[entry][px] * dL/dout[px][ch]   (K = pixels).
+// CTA = (tile, 64-channel chunk).  The dL tile is copied once into shared memory in its native
+// [channel][pixel] order by cp.async row pieces (no transposing stores); warp w owns entries
+// 16w..16w+15 of each 128-entry pass and streams their weight rows through a private double-buffered
+// slab [16][32 px].  Lane = (eg, cg) accumulates entries {eg + 4j} x channels {cg + 8k} (interleaved so
+// that both operand reads are bank-conflict free); one K step covers 4 pixels with LDS.128 of both
+// operands, and the packed FMAs pair (even, odd) pixels — no register duplication, the two halves are
+// added at the end.
 template <int CH>
 __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H, int C,
                                                                    const float* __restrict__ dL_dpixels,
                                                                    PoolView pool, float* __restrict__ dL_dcolors) {
     static_assert(CH == 64, "64-channel chunks");
-    constexpr int PITCH = CH + 4;  // floats per pixel row of the smem dL tile (keeps 16-byte alignment)
-    constexpr int WP = 36;         // pitch of the per-warp weight slab rows (32 px + pad)
+    constexpr int DP = SGB_TILE_PIX + 4;  // pitch of a channel row of the dL tile
+    constexpr int WP = 36;                // pitch of the per-warp weight slab rows (32 px + pad)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float(*dLs)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem_raw);
-    float* wslab = reinterpret_cast<float*>(smem_raw + sizeof(float) * SGB_TILE_PIX * PITCH);
+    float(*dLs)[DP] = reinterpret_cast<float(*)[DP]>(smem_raw);
+    float* wslab = reinterpret_cast<float*>(smem_raw + sizeof(float) * CH * DP);
     __shared__ const float* Wrow[128];
     __shared__ uint32_t Gid[128];
 
@@ -1022,22 +1027,29 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     if (n == 0) return;
     const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
     const size_t plane = (size_t)H * W;
-    // dL tile -> smem [px][ch]: a thread reads the 16 pixels of one tile row of one channel (64 B);
-    // lanes take consecutive channels so the transposing stores are bank-conflict free
-    for (int idx = tid; idx < CH * SGB_TILE; idx += kThreads) {
-        const int c = idx % CH, r = idx / CH;
-        const uint32_t y = pix_min.y + r;
-        const bool ok = c < nch && y < (uint32_t)H;
-        const float* src = dL_dpixels + (size_t)(ch0 + c) * plane + (size_t)W * y + pix_min.x;
+    const bool rows16 = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0;
+    // dL tile -> smem [ch][px]: 16-byte pieces (4 pixels of one tile row of one channel)
+    for (int idx = tid; idx < CH * SGB_TILE * 4; idx += kThreads) {
+        const int pc = idx & 3, r = (idx >> 2) & (SGB_TILE - 1), c = idx >> 6;
+        const uint32_t y = pix_min.y + r, x = pix_min.x + pc * 4;
+        float* dst = &dLs[c][r * SGB_TILE + pc * 4];
+        const float* src = dL_dpixels + (size_t)(ch0 + c) * plane + (size_t)W * y + x;
+        const bool rowok = c < nch && y < (uint32_t)H;
+        if (rows16) {
+            const bool ok = rowok && x + 4 <= (uint32_t)W;
+            cp_async16(dst, ok ? src : dL_dpixels, ok ? 16 : 0);
+        } else {
 #pragma unroll
-        for (int x = 0; x < SGB_TILE; x++)
-            dLs[r * SGB_TILE + x][c] = (ok && pix_min.x + x < (uint32_t)W) ? __ldg(src + x) : 0.f;
+            for (int i = 0; i < 4; i++) dst[i] = (rowok && x + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
+        }
     }
+    cp_async_commit();
+
     const int eg = lane >> 3, cg = lane & 7;
     uint32_t c0 = pool.head[tile];
     for (uint32_t base = 0; base < n; base += 128) {
         const int cnt = (int)min(128u, n - base);
-        __syncthreads();  // dLs ready (first pass) / previous pass done with Wrow, Gid
+        __syncthreads();  // previous pass done with Wrow / Gid
         if (tid < cnt) {
             const uint32_t c = chunk_at(pool, c0, tid);
             const WChunk* ck = pool.chunks + c;
@@ -1045,12 +1057,9 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
             Wrow[tid] = &ck->w[s][0];
             Gid[tid] = ck->meta[s].x;
         }
-        __syncthreads();
-        const int e0 = warp * 16 + eg * 4;  // this lane's 4 entries
+        cp_async_wait<0>();
+        __syncthreads();  // Wrow / Gid visible; dL tile landed (first pass)
         if (warp * 16 < cnt) {
-            // Weight rows stream through a private double-buffered slab [16 entries][32 px] filled with
-            // cp.async (4 x 16 B per lane per slab): the direct-load version waited a DRAM/L2 round trip
-            // on every K step (ncu: long_scoreboard 10 stalls per issue, 18 % issue utilisation).
             float(*wsl)[16][WP] = reinterpret_cast<float(*)[16][WP]>(wslab + (size_t)warp * 2 * 16 * WP);
             const float* lrow[4];
 #pragma unroll
@@ -1061,11 +1070,11 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                     cp_async16(&wsl[buf][(lane >> 3) + 4 * i][(lane & 7) * 4], lrow[i] + sl * 32, 16);
                 cp_async_commit();
             };
-            float2 acc[4][4];
+            float2 acc[4][8];  // [entry eg+4j][channel cg+8k], .x even pixels, .y odd pixels
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
-                for (int k = 0; k < 4; k++) acc[j][k] = make_float2(0.f, 0.f);
+                for (int k = 0; k < 8; k++) acc[j][k] = make_float2(0.f, 0.f);
             issue(0, 0);
             for (int sl = 0; sl < SGB_TILE_PIX / 32; sl++) {
                 const int buf = sl & 1;
@@ -1076,20 +1085,15 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                 for (int p4 = 0; p4 < 8; p4++) {
                     float4 wq[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) wq[j] = *reinterpret_cast<const float4*>(&wsl[buf][eg * 4 + j][p4 * 4]);
+                    for (int j = 0; j < 4; j++) wq[j] = *reinterpret_cast<const float4*>(&wsl[buf][eg + 4 * j][p4 * 4]);
+                    const int px = sl * 32 + p4 * 4;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int px = sl * 32 + p4 * 4 + u;
-                        const float4 d0 = *reinterpret_cast<const float4*>(&dLs[px][cg * 8]);
-                        const float4 d1 = *reinterpret_cast<const float4*>(&dLs[px][cg * 8 + 4]);
-                        const float2 dd[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y),
-                                              make_float2(d1.z, d1.w)};
+                    for (int k = 0; k < 8; k++) {
+                        const float4 d = *reinterpret_cast<const float4*>(&dLs[cg + 8 * k][px]);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const float wj = u == 0 ? wq[j].x : u == 1 ? wq[j].y : u == 2 ? wq[j].z : wq[j].w;
-                            const float2 w2 = make_float2(wj, wj);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) acc[j][k] = ffma2(dd[k], w2, acc[j][k]);
+                            acc[j][k] = ffma2(make_float2(wq[j].x, wq[j].y), make_float2(d.x, d.y), acc[j][k]);
+                            acc[j][k] = ffma2(make_float2(wq[j].z, wq[j].w), make_float2(d.z, d.w), acc[j][k]);
                         }
                     }
                 }
@@ -1097,18 +1101,12 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (e0 + j < cnt && cg * 8 < nch) {
-                    float* dst = dL_dcolors + (size_t)Gid[e0 + j] * C + ch0 + cg * 8;
-                    if (cg * 8 + 8 <= nch && (C & 3) == 0) {
-                        red_add_v4_f32(dst, make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y));
-                        red_add_v4_f32(dst + 4, make_float4(acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y));
-                    } else {
-                        const float v[8] = {acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y,
-                                            acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y};
+                const int e = warp * 16 + eg + 4 * j;
+                if (e < cnt) {
+                    float* dst = dL_dcolors + (size_t)Gid[e] * C + ch0;
 #pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            if (cg * 8 + k < nch) red_add_f32(dst + k, v[k]);
-                    }
+                    for (int k = 0; k < 8; k++)
+                        if (cg + 8 * k < nch) red_add_f32(dst + cg + 8 * k, acc[j][k].x + acc[j][k].y);
                 }
             }
         }
@@ -1137,6 +1135,7 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
         smem_raw + sizeof(float) * (8 * kSeg * 32 + 2 * CK * FP));  // per-warp dL slabs, 2 x 2 KB each
     __shared__ const float* Wrow[kSeg];
     __shared__ uint2 Meta[kSeg];
+    __shared__ float4 RecA[kSeg], RecB[kSeg];
 
     const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
     const int tile = blockIdx.x;
@@ -1182,7 +1181,11 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
                 const WChunk* ck = pool.chunks + c;
                 const int s = (base + tid) & (kChunkEntries - 1);
                 Wrow[tid] = &ck->w[s][0];
-                Meta[tid] = ck->meta[s];
+                const uint2 mt = ck->meta[s];
+                Meta[tid] = mt;
+                const float4* rp = reinterpret_cast<const float4*>(rec + mt.x);
+                RecA[tid] = __ldg(rp);
+                RecB[tid] = __ldg(rp + 1);
             } else {
                 Meta[tid] = make_uint2(0u, 0u);
             }
@@ -1280,13 +1283,17 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
         __syncwarp();
 
         // back-to-front chain over the segment (backward.cu:477-550 in dot-product form)
+        // own-pixel weights are prefetched two entries ahead (the only global load left in this loop)
+        float wn0 = __ldg(Wrow[cnt - 1] + woff);
+        float wn1 = cnt > 1 ? __ldg(Wrow[cnt - 2] + woff) : 0.f;
         for (int li = cnt - 1; li >= 0; li--) {
+            const float w = wn0;
+            wn0 = wn1;
+            if (li >= 2) wn1 = __ldg(Wrow[li - 2] + woff);
             const uint2 meta = Meta[li];
             if (!((meta.y >> warp) & 1u)) continue;
-            const float w = __ldg(Wrow[li] + woff);
             const float sdot = S[warp][li][lane];
-            const float4* rp = reinterpret_cast<const float4*>(rec + meta.x);
-            const float4 a = __ldg(rp), con_o = __ldg(rp + 1);
+            const float4 a = RecA[li], con_o = RecB[li];
             float gv[8];
 #pragma unroll
             for (int v = 0; v < 8; v++) gv[v] = 0.f;
@@ -1353,6 +1360,14 @@ size_t pool_bytes(int tiles, uint32_t chunks, PoolView* v, void* base) {
 static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
                           float* out_depth, PoolView* pv, cudaStream_t s) {
     const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    // The pool still holds this view's weight rows when the backward directly follows its forward on
+    // the same ctx (the usual training step): same binning state, same sizes, nothing ran in between.
+    if (ctx->pool_valid && ctx->pool_key_bin == (const void*)b.point_list && ctx->pool_key_R == R &&
+        ctx->pool_key_W == in.W && ctx->pool_key_H == in.H && ctx->pool_key_P == in.P && !out_depth) {
+        pool_bytes(tiles, ctx->pool_key_chunks, pv, ctx->pool.p);
+        return SGB_OK;
+    }
+    ctx->pool_valid = false;
     // first guess: ~8 chunks (128 touching Gaussians) per tile, bounded by the instance count
     uint64_t guess = (uint64_t)tiles * 8;
     const uint64_t by_R = (uint64_t)(R / kChunkEntries) + (uint64_t)tiles;
@@ -1389,6 +1404,13 @@ static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Ge
         const uint32_t used = h[0], overflow = h[1];
         if (!overflow) {
             if (used > ctx->pool_chunks_hint) ctx->pool_chunks_hint = used + used / 16 + 16;
+            ctx->pool_valid = true;
+            ctx->pool_key_bin = (const void*)b.point_list;
+            ctx->pool_key_R = R;
+            ctx->pool_key_W = in.W;
+            ctx->pool_key_H = in.H;
+            ctx->pool_key_P = in.P;
+            ctx->pool_key_chunks = chunks;
             return SGB_OK;
         }
         guess = (uint64_t)used + used / 8 + 64;  // the counter kept counting: this is the real demand
@@ -1448,7 +1470,7 @@ int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVi
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     const size_t smem = sizeof(float) * 8 * kSeg * 32;
     const size_t smem_g = smem + sizeof(float) * (2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
-    const size_t smem_d = sizeof(float) * (SGB_TILE_PIX * (64 + 4) + 8 * 2 * 16 * 36);
+    const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
     static bool attr_set = false;
     if (!attr_set) {
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_v3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -128,6 +128,12 @@ struct sgb_ctx {
     sgb::Scratch misc;     // fusion: transposed feature map, z-buffer
     sgb::Scratch pool;     // per-tile weight rows of the C-channel blend (blend_v3.cu)
     uint64_t pool_chunks_hint = 0;  // high-water mark of the pool demand (chunks)
+    // identity of the view whose weight rows the pool currently holds (forward -> backward reuse)
+    bool pool_valid = false;
+    const void* pool_key_bin = nullptr;
+    int64_t pool_key_R = 0;
+    int pool_key_W = 0, pool_key_H = 0, pool_key_P = 0;
+    uint32_t pool_key_chunks = 0;
     int64_t* pinned = nullptr;  // host-pinned readback slot(s)
     // cached layout of the last sgb_forward_geometry call (consumed by sgb_forward_render)
     int64_t last_P = 0;
