@@ -234,6 +234,7 @@ def run_gpu(args, rank, world, local_rank):
     host_labels = [torch.from_numpy(rng.integers(0, NUM_CLASSES, size=(HEIGHT, WIDTH), dtype=np.int64)
                                     .astype(np.int32)).pin_memory() for _ in range(2)]
     class_emb = torch.nn.functional.normalize(torch.randn(NUM_CLASSES, CHANNELS, device=dev), dim=1)
+    class_emb_t = (-class_emb.t() / (CHANNELS * HEIGHT * WIDTH)).contiguous()   # (C, K), pre-scaled
     dL_fixed = torch.randn((CHANNELS, HEIGHT, WIDTH), device=dev) / (HEIGHT * WIDTH)
     flat_small = None
 
@@ -269,9 +270,10 @@ def run_gpu(args, rank, world, local_rank):
         cam_dev.full_proj_transform = cam_buf[16:32].view(4, 4)
         cam_dev.camera_center = cam_buf[32:35]
         out = render_chn(cam_dev, pc, Pipe, bg, num_channels=CHANNELS, override_color=feats)
-        target = class_emb[label_buf.long().view(-1)].t().reshape(CHANNELS, HEIGHT, WIDTH)
-        loss = -(out["render"] * target).mean()                           # open-vocabulary distillation loss
-        loss.backward()
+        # open-vocabulary distillation loss  L = -mean_p <render[:, p], E[label(p)]>  and its gradient
+        dL = class_emb_t.index_select(1, label_buf.view(-1).long()).view(CHANNELS, HEIGHT, WIDTH)
+        loss = torch.dot(out["render"].detach().reshape(-1), dL.reshape(-1))
+        out["render"].backward(dL)
         allreduce_grads()
         val = loss.item()                                                  # D2H 4 B (synchronises)
         zero_grads()
