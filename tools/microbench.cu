@@ -70,6 +70,78 @@ __global__ void k_blendlike(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// register-tiled outer product like blend_forward_tma_kernel's inner loop: per step 2+2 LDS.128,
+// 8 px x 8 ch accumulators, 32 FFMA2
+__global__ void __launch_bounds__(256, 2) k_tile8x8(float* out, int iters) {
+    __shared__ __align__(16) float wsm[16][256];
+    __shared__ __align__(16) float fsm[16][64];
+    for (int e = threadIdx.x; e < 16 * 256; e += blockDim.x) (&wsm[0][0])[e] = (e % 97) * 1e-3f;
+    for (int e = threadIdx.x; e < 16 * 64; e += blockDim.x) (&fsm[0][0])[e] = (e % 31) * 1e-2f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pg = lane >> 3, cg = lane & 7;
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[i][k] = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int it = 0; it < iters; it++) {
+        const int e = it & 15;
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[e][warp * 32 + pg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[e][warp * 32 + pg * 8 + 4]);
+        const float4 f0 = *reinterpret_cast<const float4*>(&fsm[e][cg * 8]);
+        const float4 f1 = *reinterpret_cast<const float4*>(&fsm[e][cg * 8 + 4]);
+        const float2 f[4] = {make_float2(f0.x, f0.y), make_float2(f0.z, f0.w), make_float2(f1.x, f1.y), make_float2(f1.z, f1.w)};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += acc[i][k].x + acc[i][k].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// same with scalar FFMA (no packing, no duplication moves)
+__global__ void __launch_bounds__(256, 2) k_tile8x8_scalar(float* out, int iters) {
+    __shared__ __align__(16) float wsm[16][256];
+    __shared__ __align__(16) float fsm[16][64];
+    for (int e = threadIdx.x; e < 16 * 256; e += blockDim.x) (&wsm[0][0])[e] = (e % 97) * 1e-3f;
+    for (int e = threadIdx.x; e < 16 * 64; e += blockDim.x) (&fsm[0][0])[e] = (e % 31) * 1e-2f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pg = lane >> 3, cg = lane & 7;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[i][k] = 0.f;
+#pragma unroll 4
+    for (int it = 0; it < iters; it++) {
+        const int e = it & 15;
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[e][warp * 32 + pg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[e][warp * 32 + pg * 8 + 4]);
+        const float4 f0 = *reinterpret_cast<const float4*>(&fsm[e][cg * 8]);
+        const float4 f1 = *reinterpret_cast<const float4*>(&fsm[e][cg * 8 + 4]);
+        const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[i][k] = fmaf(f[k], wv[i], acc[i][k]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += acc[i][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -108,6 +180,14 @@ int main() {
         float ms = time_ms([&] { k_blendlike<CH><<<blocks, threads>>>(out, iters); });
         double fl = 2.0 * CH * (double)iters * blocks * threads;
         printf("blend-like (LDS.128 broadcast + FFMA2, CH %d): %.3f ms  %.1f TFLOP/s\n", CH, ms, fl / ms * 1e-9);
+    }
+    {
+        const int it2 = 8192;
+        float ms = time_ms([&] { k_tile8x8<<<sms * 2, 256>>>(out, it2); });
+        double fl = 2.0 * 64 * (double)it2 * sms * 2 * 256;
+        printf("8x8 register tile, FFMA2, 2 CTA/SM x 8 warps: %.3f ms  %.1f TFLOP/s\n", ms, fl / ms * 1e-9);
+        ms = time_ms([&] { k_tile8x8_scalar<<<sms * 2, 256>>>(out, it2); });
+        printf("8x8 register tile, FFMA,  2 CTA/SM x 8 warps: %.3f ms  %.1f TFLOP/s\n", ms, fl / ms * 1e-9);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
