@@ -191,9 +191,13 @@ int sgb_forward_render(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rend
     rc = run_binning(ctx, *in, num_rendered, g, b, im, radii, s);
     if (rc) return rc;
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:324
-    const char* impl = getenv("SGB_BLEND_IMPL");  // diagnostics: "v2" = fused chain+accumulate per chunk
-    if (in->C > 4 && !out_depth && !(impl && impl[0] == 'v' && impl[1] == '2'))
+    if (in->C > 4) {
+        if (out_depth) {
+            set_error("out_depth is only produced by the 3-channel RGB-D path (C <= 4)");
+            return SGB_E_INVALID;
+        }
         return blend_forward_v3(ctx, *in, num_rendered, g, b, im, colors, out_color, s);
+    }
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
     return launch_blend_forward(*in, g, b, im, colors, out_color, out_depth, s);
@@ -216,8 +220,7 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
     BinView b = BinView::carve(const_cast<void*>(binning_state), num_rendered);
     ImgView im = ImgView::carve(const_cast<void*>(image_state), in->W, in->H);
     const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:394
-    const char* impl = getenv("SGB_BLEND_IMPL");
-    if (num_rendered > 0 && in->C > 4 && !(impl && impl[0] == 'v' && impl[1] == '2')) {
+    if (num_rendered > 0 && in->C > 4) {
         rc = blend_backward_v3(ctx, *in, num_rendered, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic,
                                gr->dL_dopacity, gr->dL_dcolors, s);
         if (rc) return rc;

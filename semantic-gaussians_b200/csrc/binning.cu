@@ -19,18 +19,16 @@ namespace sgb {
 
 namespace {
 
-// tiles_touched in depth order, as an input iterator for the scan (no materialised gather).
-struct PermutedCount {
-    const uint32_t* perm;
-    const uint32_t* tiles_touched;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& i) const {
-        return tiles_touched[perm[i]];
-    }
-};
-
 __global__ void iota_kernel(int P, uint32_t* v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) v[i] = i;
+}
+
+// tiles_touched in depth order (input of the offsets scan)
+__global__ void gather_counts_kernel(int P, const uint32_t* __restrict__ perm,
+                                     const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) out[i] = tiles_touched[perm[i]];
 }
 
 // One warp handles 32 consecutive slots of the depth order; for each visible Gaussian its lanes
@@ -133,12 +131,7 @@ int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g
     size_t sort_tmp = 0, scan_tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, P, 0, 32, s);
-    {
-        cub::CountingInputIterator<uint32_t> cnt(0);
-        PermutedCount op{nullptr, nullptr};
-        cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> it(cnt, op);
-        cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, it, (uint32_t*)nullptr, P, s);
-    }
+    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, P, s);
     size_t arr = align_up(sizeof(uint32_t) * (size_t)P);
     size_t tmp = align_up(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
     int rc = ctx->geom.ensure(5 * arr + tmp);
@@ -168,10 +161,11 @@ int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g
     {
         StageTimer t(ctx, ST_SCAN, s);
         ctx->lib_launches += 1;
-        cub::CountingInputIterator<uint32_t> cnt(0);
-        PermutedCount op{perm, g.tiles_touched};
-        cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> it(cnt, op);
-        SGB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_tmp, it, offsets, P, s));
+        ctx->launches += 1;
+        // keys_in is free after the sort: reuse it for the permuted counts
+        gather_counts_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, perm, g.tiles_touched, keys_in);
+        SGB_LAUNCH_CHECK("gather_counts_kernel", in.debug, s);
+        SGB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_tmp, keys_in, offsets, P, s));
     }
     uint32_t* h = (uint32_t*)ctx->pinned;
     SGB_CUDA(cudaMemcpyAsync(h, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -1,7 +1,7 @@
-// Per-tile back-to-front blend backward for ANY channel count.  Contract: reference
-// backward.cu:394-552 (which ships for C == 3 only; written generically in C).
+// Per-tile back-to-front blend backward for the RGB / RGB-D path (C <= 4).  Contract: reference
+// backward.cu:394-552.  (Wider rasters: blend_v3.cu.)
 //
-// Decomposition: one CTA per (tile, channel chunk), thread = pixel, like the forward.  The
+// Decomposition: one CTA per tile, thread = pixel, like the forward.  The
 // reference keeps accum_rec[C], last_color[C], dL_dpixel[C] per thread (backward.cu:444-451) and
 // issues 9 + C global atomics per (pixel, Gaussian) pair (:519, :540-549).  Here
 //   * dL/dalpha is linear in dL_dpixel, so each channel chunk contributes an independent partial
@@ -248,314 +248,6 @@ __global__ void __launch_bounds__(kThreads) blend_backward_kernel(
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// v2: warp-autonomous register-tiled backward for wide chunks (CH = 32 or 64).
-//
-// A warp owns 32 pixels (two tile rows) x CH channels of dL/dout, held in registers as 8 px x MCH ch
-// micro-tiles: lane = (pg, cg) with pg = lane>>3 the pixel group (8 consecutive x of one row) and
-// cg = lane&7 the channel group.  Per staged Gaussian the two C-wide contractions are register-tile
-// products with ONE shared-memory feature fragment (2 x LDS.128) per 64 FMAs per lane:
-//     s[px]   = sum_ch F[g][ch] * dL[px][ch]   partial over the lane's MCH channels, then a 7-step
-//               transposed shuffle reduce over the 8 channel groups leaves s(px) in lane px;
-//     dF[ch]  = sum_px w[px]   * dL[px][ch]   partial over the lane's 8 pixels, then a transposed
-//               reduce over the 4 pixel groups leaves MCH/4 channel totals per lane.
-// Between them lane = pixel runs the scalar alpha/T chain exactly as v1 (and as the reference).
-// Compared with v1 (thread = pixel, broadcast feature loads, 31-step butterfly per Gaussian) this
-// removes the shared-memory bandwidth bound of the dot product (16 LDS.128 -> 2) and most of the
-// shuffle traffic of the dF reduction.
-template <int N>
-__device__ __forceinline__ void xreduce_step(float (&v)[8], int lane, int step) {
-    // halve the N live values across the lane pair (lane, lane^step): upper lanes keep the upper half
-    const bool upper = (lane & step) != 0;
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) {
-        const float send = upper ? v[i] : v[i + N / 2];
-        const float keep = upper ? v[i + N / 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-    }
-}
-
-template <int CH>
-struct __align__(16) BwdSmem2 {
-    float4 recA[2][kBatchB];
-    float4 recB[2][kBatchB];
-    uint32_t ids[2][kBatchB];
-    float feat[2][kBatchB][CH];
-    float dF[kWarps][kBatchB][CH];
-    float geo[kWarps][kBatchB][8];
-    float wx[kWarps][32];
-    uint32_t active[kWarps];
-};
-
-template <int CH, bool BULK>
-__global__ void __launch_bounds__(kThreads, 2) blend_backward_v2_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int C,
-    const float* __restrict__ bg_color, const SplatRec* __restrict__ rec, const float* __restrict__ colors,
-    const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-    const uint32_t* __restrict__ tile_last, const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D,
-    float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
-    constexpr int MCH = CH / 8;  // channels per lane micro-tile (8 for CH=64, 4 for CH=32)
-    static_assert(MCH == 4 || MCH == 8, "CH must be 32 or 64");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem2<CH>& sm = *reinterpret_cast<BwdSmem2<CH>*>(smem_raw);
-    __shared__ uint64_t bar[2];
-
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int tile = blockIdx.x;
-    const int ch0 = blockIdx.y * CH;
-    const int nch = min(CH, C - ch0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-    // own pixel (scalar chain): same mapping as thread = pixel; it is micro-tile pixel `cg` of group pg
-    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
-    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
-    const uint32_t pix_id = W * pix.y + pix.x;
-    const float2 pixf = {(float)pix.x, (float)pix.y};
-    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
-    const uint2 range = ranges[tile];
-    const int total = (int)min(tile_last[tile], range.y - range.x);
-    const int nbatches = (total + kBatchB - 1) / kBatchB;
-    if (nbatches == 0) return;
-
-    if (tid == 0 && BULK) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    if (nch < CH)
-        for (int e = tid; e < 2 * kBatchB * CH; e += kThreads) {
-            const int k = e % CH;
-            if (k >= nch) (&sm.feat[0][0][0])[e] = 0.f;
-        }
-    __syncthreads();
-
-    auto issue = [&](int b) {
-        const int st = b & 1;
-        const int hi = total - b * kBatchB;
-        const int cnt = min(kBatchB, hi);
-        if (BULK) {
-            if (tid == 0) mbar_arrive_expect_tx(&bar[st], (uint32_t)cnt * (32u + (uint32_t)nch * 4u));
-            if (tid < cnt) {
-                const uint32_t id = point_list[range.x + hi - 1 - tid];
-                sm.ids[st][tid] = id;
-                bulk_g2s(&sm.recA[st][tid], reinterpret_cast<const float4*>(rec + id), 16, &bar[st]);
-                bulk_g2s(&sm.recB[st][tid], reinterpret_cast<const float4*>(rec + id) + 1, 16, &bar[st]);
-                bulk_g2s(&sm.feat[st][tid][0], colors + (size_t)id * C + ch0, (uint32_t)nch * 4u, &bar[st]);
-            }
-        } else {
-            if (tid < cnt) {
-                const uint32_t id = point_list[range.x + hi - 1 - tid];
-                sm.ids[st][tid] = id;
-                const float4* rp = reinterpret_cast<const float4*>(rec + id);
-                sm.recA[st][tid] = __ldg(rp);
-                sm.recB[st][tid] = __ldg(rp + 1);
-            }
-            for (int e = tid; e < cnt * nch; e += kThreads) {
-                const int j = e / nch, k = e - j * nch;
-                const uint32_t id = point_list[range.x + hi - 1 - j];
-                sm.feat[st][j][k] = __ldg(colors + (size_t)id * C + ch0 + k);
-            }
-        }
-    };
-    issue(0);
-
-    // dL/dout micro-tile: dLm[i][k] = dL_dpixels[ch0 + cg*MCH + k][row][col0 + i]
-    float dLm[8][MCH];
-    {
-        const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-        const uint32_t col0 = pix_min.x + (pg & 1) * 8;
-        const size_t plane = (size_t)H * W;
-#pragma unroll
-        for (int k = 0; k < MCH; k++) {
-            const int ch = ch0 + cg * MCH + k;
-            const float* src = dL_dpixels + (size_t)ch * plane + (size_t)W * row + col0;
-            const bool chok = (cg * MCH + k) < nch && row < (uint32_t)H;
-#pragma unroll
-            for (int i = 0; i < 8; i++) dLm[i][k] = (chok && col0 + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
-        }
-    }
-    // background term of the own pixel, chunk partial (backward.cu:527-529)
-    float bgdot;
-    {
-        float part[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) part[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < MCH; k++) {
-            const float b = (cg * MCH + k) < nch ? bg_color[ch0 + cg * MCH + k] : 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) part[i] += b * dLm[i][k];
-        }
-        xreduce_step<8>(part, lane, 4);
-        xreduce_step<4>(part, lane, 2);
-        xreduce_step<2>(part, lane, 1);
-        bgdot = part[0];
-    }
-    const float T_final = inside ? final_Ts[pix_id] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-    float last_alpha = 0.f, s_last = 0.f, A = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-
-    for (int b = 0; b < nbatches; b++) {
-        const int st = b & 1;
-        const int hi = total - b * kBatchB;
-        const int cnt = min(kBatchB, hi);
-        __syncthreads();
-        if (b + 1 < nbatches) issue(b + 1);
-        if (BULK) mbar_wait(&bar[st], (uint32_t)((b >> 1) & 1));
-        __syncthreads();
-        uint32_t my_active = 0;
-
-        for (int j = 0; j < cnt; j++) {
-            const int pos = hi - 1 - j;
-            const float4 a = sm.recA[st][j];
-            const float4 con_o = sm.recB[st][j];
-            const float2 d = {a.x - pixf.x, a.y - pixf.y};
-            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-            const float G = exp(power);
-            const float alpha = min(0.99f, con_o.w * G);
-            const bool contributes = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(0xffffffffu, contributes)) continue;
-
-            // ---- s = <feature chunk, dL/dout chunk> for the own pixel
-            float part[8];
-            {
-                float f[MCH];
-                const float4* fp = reinterpret_cast<const float4*>(&sm.feat[st][j][cg * MCH]);
-#pragma unroll
-                for (int q = 0; q < MCH / 4; q++) {
-                    const float4 t = fp[q];
-                    f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; i++) part[i] = f[0] * dLm[i][0];
-#pragma unroll
-                for (int k = 1; k < MCH; k++)
-#pragma unroll
-                    for (int i = 0; i < 8; i++) part[i] = fmaf(f[k], dLm[i][k], part[i]);
-            }
-            xreduce_step<8>(part, lane, 4);
-            xreduce_step<4>(part, lane, 2);
-            xreduce_step<2>(part, lane, 1);
-            const float s = part[0];
-
-            // ---- scalar chain of the own pixel (backward.cu:498-549 in dot-product form)
-            float w = 0.f;
-            float gv[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) gv[q] = 0.f;
-            if (contributes) {
-                T = T / (1.f - alpha);
-                w = alpha * T;
-                A = last_alpha * s_last + (1.f - last_alpha) * A;
-                s_last = s;
-                float dL_dalpha = (s - A) * T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                const float dL_dG = con_o.w * dL_dalpha;
-                const float gdx = G * d.x, gdy = G * d.y;
-                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
-                gv[1] = dL_dG * dG_ddely * ddely_dy;
-                gv[2] = -0.5f * gdx * d.x * dL_dG;
-                gv[3] = -0.5f * gdx * d.y * dL_dG;
-                gv[4] = -0.5f * gdy * d.y * dL_dG;
-                gv[5] = G * dL_dalpha;
-            }
-            // geometry partials: 8 values x 32 lanes -> value q in lanes with (lane&7)==q, then over pg
-            xreduce_step<8>(gv, lane, 4);
-            xreduce_step<4>(gv, lane, 2);
-            xreduce_step<2>(gv, lane, 1);
-            float gq = gv[0];
-            gq += __shfl_xor_sync(0xffffffffu, gq, 8);
-            gq += __shfl_xor_sync(0xffffffffu, gq, 16);
-            if (lane < 6) sm.geo[warp][j][lane] = gq;
-
-            // ---- dF chunk = sum over the warp's pixels of w * dL/dout
-            sm.wx[warp][lane] = w;
-            __syncwarp();
-            float wv[8];
-            {
-                const float4 w0 = *reinterpret_cast<const float4*>(&sm.wx[warp][pg * 8]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&sm.wx[warp][pg * 8 + 4]);
-                wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
-                wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
-            }
-            __syncwarp();
-            float pdf[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) pdf[k] = 0.f;
-#pragma unroll
-            for (int k = 0; k < MCH; k++) {
-                pdf[k] = wv[0] * dLm[0][k];
-#pragma unroll
-                for (int i = 1; i < 8; i++) pdf[k] = fmaf(wv[i], dLm[i][k], pdf[k]);
-            }
-            if (MCH == 8) {
-                xreduce_step<8>(pdf, lane, 16);
-                xreduce_step<4>(pdf, lane, 8);
-                *reinterpret_cast<float2*>(&sm.dF[warp][j][cg * 8 + pg * 2]) = make_float2(pdf[0], pdf[1]);
-            } else {
-                xreduce_step<4>(pdf, lane, 16);
-                xreduce_step<2>(pdf, lane, 8);
-                sm.dF[warp][j][cg * 4 + pg] = pdf[0];
-            }
-            my_active |= 1u << j;
-        }
-        if (lane == 0) sm.active[warp] = my_active;
-        __syncthreads();
-
-        for (int e = tid; e < cnt * CH; e += kThreads) {
-            const int j = e / CH, k = e - j * CH;
-            if (k >= nch) continue;
-            float t = 0.f;
-            bool any = false;
-#pragma unroll
-            for (int wv2 = 0; wv2 < kWarps; wv2++)
-                if (sm.active[wv2] >> j & 1u) { t += sm.dF[wv2][j][k]; any = true; }
-            if (any) red_add_f32(dL_dcolors + (size_t)sm.ids[st][j] * C + ch0 + k, t);
-        }
-        for (int e = tid; e < cnt * 6; e += kThreads) {
-            const int j = e / 6, q = e - j * 6;
-            float t = 0.f;
-            bool any = false;
-#pragma unroll
-            for (int wv2 = 0; wv2 < kWarps; wv2++)
-                if (sm.active[wv2] >> j & 1u) { t += sm.geo[wv2][j][q]; any = true; }
-            if (any) {
-                const size_t id = sm.ids[st][j];
-                float* dst = q < 2 ? dL_dmean2D + id * 3 + q
-                           : q < 5 ? dL_dconic2D + id * 4 + (q == 4 ? 3 : q - 2)
-                                   : dL_dopacity + id;
-                red_add_f32(dst, t);
-            }
-        }
-    }
-}
-
-template <int CH, bool BULK>
-int launch_v2(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
-              const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
-              cudaStream_t s) {
-    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
-    const int chunks = (in.C + CH - 1) / CH;
-    const size_t smem = sizeof(BwdSmem2<CH>);
-    auto kern = blend_backward_v2_kernel<CH, BULK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    kern<<<dim3(tiles, chunks), kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, in.C, in.background, g.rec,
-                                                    colors, im.final_T, im.n_contrib, im.tile_last, dL_dpix,
-                                                    dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
-    SGB_LAUNCH_CHECK("blend_backward_v2_kernel", in.debug, s);
-    return SGB_OK;
-}
-
 template <int CH, bool BULK>
 int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
@@ -581,23 +273,11 @@ int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, con
 int launch_blend_backward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                           const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, cudaStream_t s) {
-    const bool aligned = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
-    if (in.C <= 4)
-        return launch_one<4, false>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
-    const char* force = getenv("SGB_BWD_IMPL");  // diagnostics only: "v1" selects the thread-per-pixel kernel
-    if (force && force[0] == 'v' && force[1] == '1') {
-        if (!aligned)
-            return launch_one<32, false>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
-        return launch_one<32, true>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
+    if (in.C > 4) {  // wider rasters: blend_v3.cu
+        set_error("launch_blend_backward handles C <= 4 only");
+        return SGB_E_INVALID;
     }
-    if (in.C <= 32) {
-        if (!aligned)
-            return launch_v2<32, false>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
-        return launch_v2<32, true>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
-    }
-    if (!aligned)
-        return launch_v2<64, false>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
-    return launch_v2<64, true>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
+    return launch_one<4, false>(in, g, b, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, s);
 }
 
 }  // namespace sgb

@@ -1,14 +1,11 @@
-// Per-tile front-to-back alpha compositing (forward).  Contract: reference forward.cu:262-375
-// (C-channel) and rgbd/cuda_rasterizer/forward.cu:261-393 (3 channels + median depth).
+// Per-tile front-to-back alpha compositing (forward) for the RGB / RGB-D path (C <= 4).
+// Contract: reference forward.cu:262-375 and rgbd/cuda_rasterizer/forward.cu:261-393 (median depth).
 //
-// Work decomposition: one CTA per (16x16 tile, channel chunk); thread = pixel.  The per-pixel
-// alpha / transmittance chain — the part that decides n_contrib and early termination — is the
-// reference's statement sequence verbatim, so it is bit-identical; only the colour accumulation is
-// regrouped for the chunked kernel (w = alpha*T computed once, then CH packed FMAs), which stays
-// within fp32 rounding of the reference's (f*alpha)*T.  Accumulators of a chunk live in registers
-// (the reference keeps float C[768] in local memory, forward.cu:304) and the feature slice of each
-// staged Gaussian arrives in shared memory through 1-D TMA bulk copies (cp.async.bulk + mbarrier,
-// double buffered) instead of per-thread, per-channel global loads (forward.cu:355-356).
+// One CTA per 16x16 tile, thread = pixel, Gaussians staged in shared memory per batch like the
+// reference.  The per-pixel alpha / transmittance chain and the accumulation `C[ch] += f*alpha*T`
+// are the reference's statement sequence verbatim, so pixels, depth, final_T and n_contrib are
+// bit-identical.  The kernel is templated on a channel-chunk width and a bulk-copy staging mode that
+// the wide (C > 4) path used in its first generation; that path now lives in blend_v3.cu.
 #include <cstdlib>
 #include "common.cuh"
 
@@ -178,222 +175,6 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// v2: warp-autonomous register-tiled forward for the C-channel raster (CH = 16 ... 128).
-//
-// Thread = pixel with broadcast feature loads (v1 above) needs one LDS.128 per two packed FMAs and is
-// bound by shared-memory bandwidth at half the fp32 rate (measured, tools/microbench.cu).  Here a
-// warp owns 32 pixels x CH channels of the output as 8 px x MCH ch register micro-tiles
-// (lane = (pg, cg): pixel group = 8 consecutive x of one row, channel group = MCH channels); lane =
-// pixel still runs the reference's scalar alpha / T chain verbatim, the 32 weights w = alpha*T are
-// exchanged through 128 B of shared memory, and the accumulation is an outer product
-// acc[8][MCH] += w[8] (x) f[MCH]: 2 + MCH/4 LDS.128 per 8*MCH FMAs.  Per-pixel accumulation order along
-// depth is unchanged (each accumulator still adds its Gaussians front to back).
-template <int CH, bool BULK>
-__global__ void __launch_bounds__(kThreads, (CH <= 64 ? 2 : 1)) blend_forward_v2_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int C,
-    const SplatRec* __restrict__ rec, const float* __restrict__ features, const float* __restrict__ bg_color,
-    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_last,
-    float* __restrict__ out_color) {
-    constexpr int MCH = CH / 8;
-    static_assert(MCH >= 2 && MCH % 2 == 0, "CH must be a multiple of 16");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    FwdStage<CH>* stage = reinterpret_cast<FwdStage<CH>*>(smem_raw);
-    __shared__ uint64_t bar[2];
-    __shared__ uint32_t s_last;
-    __shared__ __align__(16) float wx[kThreads / 32][32];
-
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int tile = blockIdx.x;
-    const int ch0 = blockIdx.y * CH;
-    const int nch = min(CH, C - ch0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
-    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
-    const uint32_t pix_id = W * pix.y + pix.x;
-    const float2 pixf = {(float)pix.x, (float)pix.y};
-    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
-    bool done = !inside;
-
-    const uint2 range = ranges[tile];
-    const int total = (int)(range.y - range.x);
-    const int nbatches = (total + kBatch - 1) / kBatch;
-
-    if (tid == 0) {
-        if (BULK) {
-            mbar_init(&bar[0], 1);
-            mbar_init(&bar[1], 1);
-            mbar_fence_init();
-        }
-        s_last = 0;
-    }
-    if (nch < CH)  // unused tail of a partial chunk must not inject NaNs into 0-weighted products
-        for (int e = tid; e < 2 * kBatch * CH; e += kThreads) {
-            const int st = e / (kBatch * CH), r = e % (kBatch * CH);
-            if (r % CH >= nch) stage[st].feat[r / CH][r % CH] = 0.f;
-        }
-    __syncthreads();
-
-    auto issue = [&](int b) {
-        FwdStage<CH>& st = stage[b & 1];
-        const int base = b * kBatch;
-        const int cnt = min(kBatch, total - base);
-        if (BULK) {
-            if (tid == 0) mbar_arrive_expect_tx(&bar[b & 1], (uint32_t)cnt * (32u + (uint32_t)nch * 4u));
-            if (tid < cnt) {
-                const uint32_t id = point_list[range.x + base + tid];
-                bulk_g2s(&st.recA[tid], reinterpret_cast<const float4*>(rec + id), 16, &bar[b & 1]);
-                bulk_g2s(&st.recB[tid], reinterpret_cast<const float4*>(rec + id) + 1, 16, &bar[b & 1]);
-                bulk_g2s(&st.feat[tid][0], features + (size_t)id * C + ch0, (uint32_t)nch * 4u, &bar[b & 1]);
-            }
-        } else {
-            if (tid < cnt) {
-                const uint32_t id = point_list[range.x + base + tid];
-                const float4* rp = reinterpret_cast<const float4*>(rec + id);
-                st.recA[tid] = __ldg(rp);
-                st.recB[tid] = __ldg(rp + 1);
-            }
-            for (int e = tid; e < cnt * nch; e += kThreads) {
-                const int j = e / nch, k = e - j * nch;
-                const uint32_t id = point_list[range.x + base + j];
-                st.feat[j][k] = __ldg(features + (size_t)id * C + ch0 + k);
-            }
-        }
-    };
-
-    float T = 1.0f;
-    uint32_t contributor = 0;
-    uint32_t last_contributor = 0;
-    float2 acc[8][MCH / 2];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
-
-    int issued = 0, consumed = 0;
-    if (nbatches > 0) { issue(0); issued = 1; }
-
-    for (int b = 0; b < nbatches; b++) {
-        const int num_done = __syncthreads_count(done);  // forward.cu:310-312; also the stage WAR fence
-        if (num_done == kThreads) break;
-        if (b + 1 < nbatches) { issue(b + 1); issued = b + 2; }
-        if (BULK) mbar_wait(&bar[b & 1], (uint32_t)((b >> 1) & 1));
-        else __syncthreads();
-        consumed = b + 1;
-
-        const FwdStage<CH>& st = stage[b & 1];
-        const int cnt = min(kBatch, total - b * kBatch);
-        if (__all_sync(0xffffffffu, done)) continue;  // this warp's 32 pixels are finished
-        for (int j = 0; j < cnt; j++) {
-            // ---- scalar chain of the own pixel: forward.cu:329-362 verbatim (done pixels idle)
-            float w = 0.f;
-            if (!done) {
-                contributor++;
-                const float4 a = st.recA[j];
-                const float2 xy = {a.x, a.y};
-                const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-                const float4 con_o = st.recB[j];
-                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                if (!(power > 0.0f)) {
-                    const float alpha = min(0.99f, con_o.w * exp(power));
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        const float test_T = T * (1 - alpha);
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            w = alpha * T;
-                            T = test_T;
-                            last_contributor = contributor;
-                        }
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, w != 0.f)) {
-                if (__all_sync(0xffffffffu, done)) break;
-                continue;
-            }
-            // ---- exchange the 32 weights, then acc[8 px][MCH ch] += w (x) f
-            wx[warp][lane] = w;
-            __syncwarp();
-            const float4 w0 = *reinterpret_cast<const float4*>(&wx[warp][pg * 8]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&wx[warp][pg * 8 + 4]);
-            __syncwarp();
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            const float2* fp = reinterpret_cast<const float2*>(&st.feat[j][cg * MCH]);
-            float2 f[MCH / 2];
-#pragma unroll
-            for (int k = 0; k < MCH / 2; k++) f[k] = fp[k];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float2 w2 = make_float2(wv[i], wv[i]);
-#pragma unroll
-                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
-            }
-        }
-    }
-    if (BULK && issued > consumed) mbar_wait(&bar[consumed & 1], (uint32_t)((consumed >> 1) & 1));
-
-    if (blockIdx.y == 0) {
-        if (inside) {
-            final_T[pix_id] = T;
-            n_contrib[pix_id] = last_contributor;
-            atomicMax(&s_last, last_contributor);
-        }
-        __syncthreads();
-        if (tid == 0) tile_last[tile] = s_last;
-    }
-    // epilogue: out = acc + T * bg for the lane's 8 px x MCH ch (T of the 8 pixels via the exchange buffer)
-    wx[warp][lane] = T;
-    __syncwarp();
-    const float4 t0 = *reinterpret_cast<const float4*>(&wx[warp][pg * 8]);
-    const float4 t1 = *reinterpret_cast<const float4*>(&wx[warp][pg * 8 + 4]);
-    const float Tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
-    if (row < (uint32_t)H) {
-        const size_t plane = (size_t)H * W;
-        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
-#pragma unroll
-        for (int k = 0; k < MCH; k++) {
-            const int chl = cg * MCH + k;
-            if (chl >= nch) continue;
-            const float bgc = bg_color[ch0 + chl];
-            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
-            if (vec) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
-            }
-        }
-    }
-}
-
-template <int CH, bool BULK>
-int launch_v2(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
-              float* out_color, cudaStream_t s) {
-    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
-    const int chunks = (in.C + CH - 1) / CH;
-    const size_t smem = 2 * sizeof(FwdStage<CH>);
-    auto kern = blend_forward_v2_kernel<CH, BULK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    kern<<<dim3(tiles, chunks), kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, in.C, g.rec, colors,
-                                                    in.background, im.final_T, im.n_contrib, im.tile_last, out_color);
-    SGB_LAUNCH_CHECK("blend_forward_v2_kernel", in.debug, s);
-    return SGB_OK;
-}
-
 template <int CH, bool BULK, bool EXACT, bool DEPTH>
 int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                float* out_color, float* out_depth, cudaStream_t s) {
@@ -417,30 +198,14 @@ int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, con
 
 int launch_blend_forward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                          float* out_color, float* out_depth, cudaStream_t s) {
-    const bool aligned = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
-    if (in.C <= 4) {
-        // RGB / RGB-D path: the reference's accumulation order, bit for bit.
-        if (out_depth) return launch_one<4, false, true, true>(in, g, b, im, colors, out_color, out_depth, s);
-        return launch_one<4, false, true, false>(in, g, b, im, colors, out_color, nullptr, s);
-    }
-    if (out_depth) {
-        set_error("out_depth is only produced by the 3-channel RGB-D path (C <= 4)");
+    // RGB / RGB-D path (C <= 4): the reference's accumulation order, bit for bit.  Wider rasters go
+    // through the weights-once pipeline in blend_v3.cu.
+    if (in.C > 4) {
+        set_error("launch_blend_forward handles C <= 4 only");
         return SGB_E_INVALID;
     }
-    const char* force = getenv("SGB_FWD_IMPL");  // diagnostics only: "v1" = thread-per-pixel kernel, "128" = CH 128
-    if (force && force[0] == 'v' && force[1] == '1') {
-        if (!aligned) return launch_one<32, false, false, false>(in, g, b, im, colors, out_color, nullptr, s);
-        return launch_one<64, true, false, false>(in, g, b, im, colors, out_color, nullptr, s);
-    }
-    if (!aligned) {
-        if (in.C <= 16) return launch_v2<16, false>(in, g, b, im, colors, out_color, s);
-        if (in.C <= 32) return launch_v2<32, false>(in, g, b, im, colors, out_color, s);
-        return launch_v2<64, false>(in, g, b, im, colors, out_color, s);
-    }
-    if (in.C <= 16) return launch_v2<16, true>(in, g, b, im, colors, out_color, s);
-    if (in.C <= 32) return launch_v2<32, true>(in, g, b, im, colors, out_color, s);
-    if (force && force[0] == '1') return launch_v2<128, true>(in, g, b, im, colors, out_color, s);
-    return launch_v2<64, true>(in, g, b, im, colors, out_color, s);
+    if (out_depth) return launch_one<4, false, true, true>(in, g, b, im, colors, out_color, out_depth, s);
+    return launch_one<4, false, true, false>(in, g, b, im, colors, out_color, nullptr, s);
 }
 
 }  // namespace sgb

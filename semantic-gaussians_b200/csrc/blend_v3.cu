@@ -304,13 +304,7 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
     }
 }
 
-// ------------------------------------------------------------------------------------ forward, pipelined
-// Same decomposition as blend_forward_v3_kernel, but every warp keeps RD entries in flight through
-// a private shared-memory ring filled with cp.async (one 16-byte LDGSTS per lane: lanes 0-7 the
-// warp's 32 weights, lanes 8-23 the 64-channel feature slice).  The direct-load version above waits
-// an L2 round trip per entry (ncu: long_scoreboard 12.7 stalls per issue, 23 % issue utilisation);
-// the ring hides it without spending accumulator registers on double buffering.  Entries whose
-// strip bit is clear are skipped at issue time, so the consumer only sees Gaussians that touch it.
+// ------------------------------------------------------------------------------------ async-copy helpers
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
                  : "memory");
@@ -321,398 +315,8 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Walks one tile's chunk list front to back and yields the entries whose strip bit `bit` is set
-// (bit < 0: every entry).  Lane s < 16 keeps meta[s] of the current chunk in registers.
-struct EntryCursor {
-    const WChunk* chunks;
-    uint32_t capacity;
-    const WChunk* ck;
-    uint32_t n, e0, c, nextc, act;
-    uint2 mlane;
-    __device__ __forceinline__ void load_chunk(int lane, int bit) {
-        ck = chunks + min(c, capacity - 1);
-        const int m = (int)min((uint32_t)kChunkEntries, n - e0);
-        mlane = make_uint2(0u, 0u);
-        if (lane < m) mlane = ck->meta[lane];
-        const bool on = lane < m && (bit < 0 || ((mlane.y >> bit) & 1u));
-        act = __ballot_sync(0xffffffffu, on);
-        nextc = ck->next;
-    }
-    __device__ __forceinline__ void init(const PoolView& pool, int tile, int lane, int bit) {
-        chunks = pool.chunks;
-        capacity = pool.capacity;
-        n = pool.count[tile];
-        c = pool.head[tile];
-        e0 = 0;
-        act = 0;
-        if (n) load_chunk(lane, bit);
-    }
-    // slot index (0..15) of the next selected entry inside `ck`, or -1 when the list is exhausted
-    __device__ __forceinline__ int next(int lane, int bit) {
-        while (act == 0) {
-            if (n == 0 || e0 + kChunkEntries >= n) return -1;
-            e0 += kChunkEntries;
-            c = nextc;
-            load_chunk(lane, bit);
-        }
-        const int s = __ffs(act) - 1;
-        act &= act - 1;
-        return s;
-    }
-};
 
-template <int CH, int RD>
-__global__ void __launch_bounds__(kThreads, 2) blend_forward_v3r_kernel(
-    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
-    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
-    constexpr int MCH = CH / 8;
-    constexpr int ROW = 32 + CH;  // floats per ring slot: 32 weights + CH features
-    static_assert(ROW % 4 == 0 && ROW / 4 <= 32, "one 16-byte cp.async per lane");
-    __shared__ __align__(16) float ring[kThreads / 32][RD][ROW];
-
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int nchunksC = (C + CH - 1) / CH;
-    const int tile = blockIdx.x / nchunksC;
-    const int ch0 = (blockIdx.x % nchunksC) * CH;
-    const int nch = min(CH, C - ch0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-
-    float2 acc[8][MCH / 2];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
-
-    EntryCursor cur;
-    cur.init(pool, tile, lane, warp);
-    auto issue = [&](int slot) -> bool {  // always commits exactly one group
-        const int s = cur.next(lane, warp);
-        if (s >= 0) {
-            const uint32_t gid = __shfl_sync(0xffffffffu, cur.mlane.x, s);
-            if (lane < ROW / 4) {
-                const float* src;
-                int bytes = 16;
-                if (lane < 8) {
-                    src = &cur.ck->w[s][warp * 32 + lane * 4];
-                } else {
-                    const int k = (lane - 8) * 4;
-                    src = features + (size_t)gid * C + ch0 + k;
-                    if (k >= nch) { bytes = 0; src = features; }
-                }
-                cp_async16(&ring[warp][slot][lane * 4], src, bytes);
-            }
-        }
-        cp_async_commit();
-        return s >= 0;
-    };
-
-    int issued = 0, consumed = 0;
-    bool more = true;
-#pragma unroll
-    for (int i = 0; i < RD; i++) {
-        if (more) { more = issue(i); issued += more ? 1 : 0; }
-        else cp_async_commit();
-    }
-    while (consumed < issued) {
-        cp_async_wait<RD - 1>();
-        __syncwarp();
-        const int slot = consumed % RD;
-        const float* rs = ring[warp][slot];
-        const float4 w0 = *reinterpret_cast<const float4*>(rs + pg * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(rs + pg * 8 + 4);
-        float2 f[MCH / 2];
-#pragma unroll
-        for (int q = 0; q < MCH / 4; q++) {
-            const float4 t = *reinterpret_cast<const float4*>(rs + 32 + cg * MCH + 4 * q);
-            f[2 * q] = make_float2(t.x, t.y);
-            f[2 * q + 1] = make_float2(t.z, t.w);
-        }
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float2 w2 = make_float2(wv[i], wv[i]);
-#pragma unroll
-            for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
-        }
-        consumed++;
-        __syncwarp();  // the slot is free again
-        if (more) { more = issue(slot); issued += more ? 1 : 0; }
-        else cp_async_commit();
-    }
-    cp_async_wait<0>();
-
-    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
-    if (row < (uint32_t)H) {
-        const size_t plane = (size_t)H * W;
-        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
-        float Tv[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
-#pragma unroll
-        for (int k = 0; k < MCH; k++) {
-            const int chl = cg * MCH + k;
-            if (chl >= nch) continue;
-            const float bgc = bg_color[ch0 + chl];
-            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
-            if (vec) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------ backward 1
-// s = <feature, dL/dout> over ALL channels per (pixel, entry), then the back-to-front chain.
-constexpr int kSeg = 64;  // entries per segment (4 chunks); S[8 warps][kSeg][32 lanes] = 64 KB
-
-template <int CH, bool VEC>
-__global__ void __launch_bounds__(kThreads, 2) chain_backward_v3_kernel(
-    int W, int H, int C, const float* __restrict__ bg_color, const SplatRec* __restrict__ rec,
-    const float* __restrict__ features, const float* __restrict__ final_Ts, const float* __restrict__ dL_dpixels,
-    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity) {
-    constexpr int MCH = CH / 8;
-    static_assert(MCH == 8, "chain_backward_v3 uses 64-channel passes");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float(*S)[kSeg][32] = reinterpret_cast<float(*)[kSeg][32]>(smem_raw);
-
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int tile = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
-    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
-    const uint32_t pix_id = W * pix.y + pix.x;
-    const float2 pixf = {(float)pix.x, (float)pix.y};
-    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
-    const uint32_t n = pool.count[tile];
-    if (n == 0) return;
-
-    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
-    const size_t plane = (size_t)H * W;
-    const int nchunksC = (C + CH - 1) / CH;
-    const int woff = warp * 32 + lane;
-
-    const float T_final = inside ? final_Ts[pix_id] : 0.f;
-    float T = T_final;
-    float last_alpha = 0.f, s_last = 0.f, A = 0.f, bgdot = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-
-    uint32_t remaining = n;
-    uint32_t cend = pool.tail[tile];
-    bool first = true;
-    while (remaining > 0) {
-        // segment = up to 4 chunks ending at cend (cidx[0] = last chunk of the segment)
-        uint32_t cidx[4] = {0, 0, 0, 0};
-        int cnts[4] = {0, 0, 0, 0};
-        int nck = 0, seg = 0;
-        {
-            uint32_t c = min(cend, pool.capacity - 1), r = remaining;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (r > 0) {
-                    const int m = (int)((r - 1) & (kChunkEntries - 1)) + 1;
-                    cidx[q] = c;
-                    cnts[q] = m;
-                    seg += m;
-                    r -= m;
-                    c = min(pool.chunks[c].prev, pool.capacity - 1);
-                    nck = q + 1;
-                }
-            }
-            cend = c;
-        }
-        for (int li = 0; li < seg; li++) S[warp][li][lane] = 0.f;
-
-        for (int cc = 0; cc < nchunksC; cc++) {
-            const int ch0 = cc * CH;
-            const int nch = min(CH, C - ch0);
-            float dLm[8][MCH];
-#pragma unroll
-            for (int k = 0; k < MCH; k++) {
-                const float* src = dL_dpixels + (size_t)(ch0 + cg * MCH + k) * plane + (size_t)W * row + col0;
-                const bool chok = (cg * MCH + k) < nch && row < (uint32_t)H;
-#pragma unroll
-                for (int i = 0; i < 8; i++) dLm[i][k] = (chok && col0 + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
-            }
-            if (first) {  // background term of the own pixel (backward.cu:527-529), all channels
-                float part[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) part[i] = 0.f;
-#pragma unroll
-                for (int k = 0; k < MCH; k++) {
-                    const float bgc = (cg * MCH + k) < nch ? bg_color[ch0 + cg * MCH + k] : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) part[i] += bgc * dLm[i][k];
-                }
-                xreduce_step<8>(part, lane, 4);
-                xreduce_step<4>(part, lane, 2);
-                xreduce_step<2>(part, lane, 1);
-                bgdot += part[0];
-            }
-            int li = 0;
-#pragma unroll
-            for (int q = 3; q >= 0; q--) {
-                if (q >= nck) continue;
-                const WChunk* ck = pool.chunks + cidx[q];
-                for (int s = 0; s < cnts[q]; s++, li++) {
-                    const uint2 meta = ck->meta[s];
-                    if (!((meta.y >> warp) & 1u)) continue;
-                    const float* fr = features + (size_t)meta.x * C + ch0 + cg * MCH;
-                    float f[MCH];
-                    if (VEC) {
-#pragma unroll
-                        for (int v = 0; v < MCH / 4; v++) {
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (cg * MCH + 4 * v < nch) t = __ldg(reinterpret_cast<const float4*>(fr) + v);
-                            f[4 * v] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < MCH; k++) f[k] = (cg * MCH + k < nch) ? __ldg(fr + k) : 0.f;
-                    }
-                    float part[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) part[i] = f[0] * dLm[i][0];
-#pragma unroll
-                    for (int k = 1; k < MCH; k++)
-#pragma unroll
-                        for (int i = 0; i < 8; i++) part[i] = fmaf(f[k], dLm[i][k], part[i]);
-                    xreduce_step<8>(part, lane, 4);
-                    xreduce_step<4>(part, lane, 2);
-                    xreduce_step<2>(part, lane, 1);
-                    S[warp][li][lane] += part[0];
-                }
-            }
-        }
-
-        // back-to-front chain over the segment (backward.cu:477-550 in dot-product form)
-        int li = seg - 1;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (q >= nck) continue;
-            const WChunk* ck = pool.chunks + cidx[q];
-            for (int s = cnts[q] - 1; s >= 0; s--, li--) {
-                const uint2 meta = ck->meta[s];
-                if (!((meta.y >> warp) & 1u)) continue;
-                const float w = ck->w[s][woff];
-                const float sdot = S[warp][li][lane];
-                const float4* rp = reinterpret_cast<const float4*>(rec + meta.x);
-                const float4 a = __ldg(rp), con_o = __ldg(rp + 1);
-                float gv[8];
-#pragma unroll
-                for (int v = 0; v < 8; v++) gv[v] = 0.f;
-                if (w != 0.f) {  // this pixel blended this Gaussian in the forward pass
-                    const float2 d = {a.x - pixf.x, a.y - pixf.y};
-                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                    const float G = exp(power);
-                    const float alpha = min(0.99f, con_o.w * G);
-                    T = T / (1.f - alpha);
-                    A = last_alpha * s_last + (1.f - last_alpha) * A;
-                    s_last = sdot;
-                    float dL_dalpha = (sdot - A) * T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                    const float dL_dG = con_o.w * dL_dalpha;
-                    const float gdx = G * d.x, gdy = G * d.y;
-                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                    gv[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    gv[1] = dL_dG * dG_ddely * ddely_dy;
-                    gv[2] = -0.5f * gdx * d.x * dL_dG;
-                    gv[3] = -0.5f * gdx * d.y * dL_dG;
-                    gv[4] = -0.5f * gdy * d.y * dL_dG;
-                    gv[5] = G * dL_dalpha;
-                }
-                xreduce_step<8>(gv, lane, 4);
-                xreduce_step<4>(gv, lane, 2);
-                xreduce_step<2>(gv, lane, 1);
-                float gq = gv[0];
-                gq += __shfl_xor_sync(0xffffffffu, gq, 8);
-                gq += __shfl_xor_sync(0xffffffffu, gq, 16);
-                if (lane < 6) {
-                    const size_t id = meta.x;
-                    float* dst = lane < 2 ? dL_dmean2D + id * 3 + lane
-                               : lane < 5 ? dL_dconic2D + id * 4 + (lane == 4 ? 3 : lane - 2)
-                                          : dL_dopacity + id;
-                    red_add_f32(dst, gq);
-                }
-            }
-        }
-        remaining -= (uint32_t)seg;
-        first = false;
-    }
-}
-
-// ------------------------------------------------------------------------------------ backward 2
-template <int CH>
-__global__ void __launch_bounds__(kThreads, 2) dfeature_v3_kernel(int W, int H, int C,
-                                                                 const float* __restrict__ dL_dpixels,
-                                                                 PoolView pool, float* __restrict__ dL_dcolors) {
-    constexpr int MCH = CH / 8;
-    static_assert(MCH == 8, "dfeature_v3 uses 8-channel slices per warp");
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int nchunksC = (C + CH - 1) / CH;
-    const int tile = blockIdx.x / nchunksC;
-    const int ch0 = (blockIdx.x % nchunksC) * CH;
-    const int nch = min(CH, C - ch0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = pool.count[tile];
-    if (n == 0 || warp * MCH >= nch) return;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-    // lane <-> tile pixels [8*lane, 8*lane+8): row = lane>>1, columns (lane&1)*8 ..
-    const uint32_t row = pix_min.y + (lane >> 1);
-    const uint32_t col0 = pix_min.x + (lane & 1) * 8;
-    const size_t plane = (size_t)H * W;
-    float dLm[8][MCH];
-#pragma unroll
-    for (int k = 0; k < MCH; k++) {
-        const float* src = dL_dpixels + (size_t)(ch0 + warp * MCH + k) * plane + (size_t)W * row + col0;
-        const bool chok = (warp * MCH + k) < nch && row < (uint32_t)H;
-#pragma unroll
-        for (int i = 0; i < 8; i++) dLm[i][k] = (chok && col0 + i < (uint32_t)W) ? __ldg(src + i) : 0.f;
-    }
-    uint32_t c = pool.head[tile];
-    for (uint32_t e = 0; e < n;) {
-        const WChunk* ck = pool.chunks + min(c, pool.capacity - 1);
-        const int m = (int)min((uint32_t)kChunkEntries, n - e);
-        for (int s = 0; s < m; s++) {
-            const uint2 meta = ck->meta[s];
-            const float4* wp = reinterpret_cast<const float4*>(&ck->w[s][lane * 8]);
-            const float4 w0 = wp[0], w1 = wp[1];
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            float pdf[8];
-#pragma unroll
-            for (int k = 0; k < MCH; k++) {
-                pdf[k] = wv[0] * dLm[0][k];
-#pragma unroll
-                for (int i = 1; i < 8; i++) pdf[k] = fmaf(wv[i], dLm[i][k], pdf[k]);
-            }
-            xreduce_step<8>(pdf, lane, 4);
-            xreduce_step<4>(pdf, lane, 2);
-            xreduce_step<2>(pdf, lane, 1);
-            float v = pdf[0];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 8 && warp * MCH + lane < nch)
-                red_add_f32(dL_dcolors + (size_t)meta.x * C + ch0 + warp * MCH + lane, v);
-        }
-        e += m;
-        c = ck->next;
-    }
-}
+constexpr int kSeg = 64;  // entries per backward segment (4 chunks); S[8 warps][kSeg][32 lanes] = 64 KB
 
 // ------------------------------------------------------------------------------------ GEMM-shaped kernels
 // With the weights materialised per tile, the three C-wide contractions are small dense GEMMs over the
@@ -721,12 +325,9 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_v3_kernel(int W, int H, 
 //     forward   out[256 px][64 ch]  = W^T[256 px][G]  . F[G][64 ch]      K = G      lane tile 8 px x 8 ch
 //     s-pass    S[256 px][G]        = dL[256 px][C]   . F^T[C][G]        K = C      lane tile 8 px x 8 entries
 //     dfeature  dF[G][64 ch]        = W[G][256 px]    . dL[256 px][64]   K = 256 px lane tile 4 entries x 8 ch
-// Register tiles make every product 64-128 FMAs per 4-6 shared/L1 loads and need no cross-lane
-// reductions (the shuffle-reduce variants above spend ~40 % of their issue slots on SHFL/FSEL/FADD).
+// Register tiles make every product 64-128 FMAs per 4-6 shared-memory loads and need no cross-lane
+// reductions (an earlier shuffle-reduce formulation spent ~40 % of its issue slots on SHFL/FSEL/FADD).
 constexpr int kEB = 64;  // entries per staged batch
-
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Sequential reader of a tile's entry list for whole-CTA staging: thread t < cnt gets entry base+t.
 struct BatchCursor {
@@ -744,125 +345,9 @@ __device__ __forceinline__ uint32_t chunk_at(const PoolView& pool, uint32_t c0, 
     return c;
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kThreads, 2) blend_forward_gemm_kernel(
-    int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
-    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
-    constexpr int MCH = CH / 8;
-    static_assert(CH == 64, "feature staging assumes 64-channel chunks");
-    __shared__ __align__(16) float Fs[2][kEB][CH];         // feature slices of the staged entries (2 x 16 KB)
-    __shared__ const float* Wrow[2][kEB];                  // weight row of each staged entry
-
-    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
-    const int nchunksC = (C + CH - 1) / CH;
-    const int tile = blockIdx.x / nchunksC;
-    const int ch0 = (blockIdx.x % nchunksC) * CH;
-    const int nch = min(CH, C - ch0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
-    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
-
-    float2 acc[8][MCH / 2];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
-
-    BatchCursor bc;
-    bc.init(pool, tile);
-    const int nb = (int)((bc.n + kEB - 1) / kEB);
-    // staging: thread t -> entry t>>2 of the batch, 16 channels (t&3)*16 .. +16 as 4 x cp.async(16 B)
-    auto stage = [&](int b, int buf) {
-        const int base = b * kEB;
-        const int cnt = min(kEB, (int)bc.n - base);
-        const int e = tid >> 2, q = tid & 3;
-        if (e < cnt) {
-            const uint32_t c = chunk_at(pool, bc.c0, e);
-            const WChunk* ck = pool.chunks + c;
-            const int s = (base + e) & (kChunkEntries - 1);
-            const uint32_t gid = ck->meta[s].x;
-            if (q == 0) Wrow[buf][e] = &ck->w[s][0];
-            const float* src = features + (size_t)gid * C + ch0 + q * 16;
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const int k = q * 16 + v * 4;
-                cp_async16(&Fs[buf][e][k], k < nch ? src + v * 4 : features, k < nch ? 16 : 0);
-            }
-        }
-        cp_async_commit();
-    };
-    if (nb > 0) stage(0, 0);
-    for (int b = 0; b < nb; b++) {
-        const int buf = b & 1;
-        const int cnt = min(kEB, (int)bc.n - b * kEB);
-        cp_async_wait<0>();
-        __syncthreads();  // batch b staged by everyone; batch b-1 fully consumed
-        if (b + 1 < nb) {
-            // advance the cursor to the first chunk of batch b+1 (kEB / 16 hops), uniformly
-            uint32_t c = min(bc.c0, pool.capacity - 1);
-#pragma unroll
-            for (int h = 0; h < kEB / kChunkEntries; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
-            bc.c0 = c;
-            stage(b + 1, buf ^ 1);
-        }
-        const int woff = warp * 32 + pg * 8;
-        constexpr int PF = 12;  // weight-row prefetch distance (entries); rows are L2/DRAM resident
-        if ((lane & 7) == 0)
-            for (int e = 0; e < min(PF, cnt); e++) prefetch_l1(Wrow[buf][e] + woff);
-#pragma unroll 4
-        for (int e = 0; e < cnt; e++) {
-            if ((lane & 7) == 0 && e + PF < cnt) prefetch_l1(Wrow[buf][e + PF] + woff);
-            const float4* wp = reinterpret_cast<const float4*>(Wrow[buf][e] + woff);
-            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-            float2 f[MCH / 2];
-#pragma unroll
-            for (int q = 0; q < MCH / 4; q++) {
-                const float4 t = *reinterpret_cast<const float4*>(&Fs[buf][e][cg * MCH + 4 * q]);
-                f[2 * q] = make_float2(t.x, t.y);
-                f[2 * q + 1] = make_float2(t.z, t.w);
-            }
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float2 w2 = make_float2(wv[i], wv[i]);
-#pragma unroll
-                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
-            }
-        }
-    }
-
-    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
-    if (row < (uint32_t)H) {
-        const size_t plane = (size_t)H * W;
-        const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
-        float Tv[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
-#pragma unroll
-        for (int k = 0; k < MCH; k++) {
-            const int chl = cg * MCH + k;
-            if (chl >= nch) continue;
-            const float bgc = bg_color[ch0 + chl];
-            float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k / 2].y : acc[i][k / 2].x) + Tv[i] * bgc;
-            if (vec) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (col0 + i < (uint32_t)W) dst[i] = o[i];
-            }
-        }
-    }
-}
-
-// Forward GEMM with a TMA-fed ring.  ncu on blend_forward_gemm_kernel: 67 % of the instructions are
-// packed FMAs but only 28 % of the issue slots are used — every warp waits an L2/DRAM round trip on
-// its weight loads (long_scoreboard 9.2 stalls per issue).  Here each staged Gaussian is two 1-D bulk
+// Forward GEMM with a TMA-fed ring.  With plain loads of the weight rows 67 % of the instructions were
+// packed FMAs but only 28 % of the issue slots were used — every warp waited an L2/DRAM round trip per
+// entry (ncu long_scoreboard 9.2 stalls per issue).  Here each staged Gaussian is two 1-D bulk
 // copies (cp.async.bulk: the 1 KB weight row and the 256 B feature slice) into a ring of NS stages
 // of ES entries guarded by full/empty mbarriers; warp 0 issues stage b+NS-1 after consuming stage b,
 // so up to (NS-1)*ES entries are in flight and no warp ever blocks on a global load.
@@ -1156,11 +641,8 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
     const uint32_t n = pool.count[tile];
     if (n == 0) return;
 
-    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
-    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
     const size_t plane = (size_t)H * W;
-    const bool rowok = row < (uint32_t)H;
-    const bool vec8 = rowok && ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+    const bool rows16 = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0);
     const int woff = warp * 32 + lane;
 
     // background term of the own pixel over all channels (backward.cu:527-529)
@@ -1239,9 +721,16 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
                 const int pc = lane & 7;  // 16-byte piece: tile row pc>>2 of the strip, columns (pc&3)*4..
                 const uint32_t y = pix_min.y + 2 * warp + (pc >> 2);
                 const uint32_t x = pix_min.x + (pc & 3) * 4;
-                const bool ok = ch < C && y < (uint32_t)H && x + 4 <= (uint32_t)W;
-                const float* src = ok ? dL_dpixels + (size_t)ch * plane + (size_t)W * y + x : dL_dpixels;
-                cp_async16(&DS[warp][buf][chl][pc * 4], src, ok ? 16 : 0);
+                const bool rowin = ch < C && y < (uint32_t)H;
+                const float* src = dL_dpixels + (size_t)ch * plane + (size_t)W * y + x;
+                if (rows16) {
+                    const bool ok = rowin && x + 4 <= (uint32_t)W;
+                    cp_async16(&DS[warp][buf][chl][pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
+                } else {  // image rows not 16-byte aligned: plain loads, ordered by the slab barrier
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        DS[warp][buf][chl][pc * 4 + u] = (rowin && x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
+                }
             }
             cp_async_commit();
         };
@@ -1435,8 +924,7 @@ int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVie
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
-    const char* dbg = getenv("SGB_FWD_DIRECT");  // diagnostics: 1 = direct loads, 2 = per-warp cp.async ring
-    if (vec && !dbg) {
+    if (vec) {
         constexpr int ES = 8, NS = 8;
         const size_t smem_f = (size_t)NS * (ES * (SGB_TILE_PIX + 64) + 16) * sizeof(float);
         static bool fattr = false;
@@ -1448,19 +936,12 @@ int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVie
         blend_forward_tma_kernel<64, ES, NS><<<tiles * chunks, kThreads, smem_f, s>>>(in.W, in.H, in.C, colors,
                                                                                       in.background, im.final_T, pv,
                                                                                       out_color);
-    } else if (vec && dbg[0] == '3')
-        blend_forward_gemm_kernel<64><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
-                                                                          im.final_T, pv, out_color);
-    else if (vec && dbg[0] == '2')
-        blend_forward_v3r_kernel<64, 8><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
-                                                                            im.final_T, pv, out_color);
-    else if (vec)
-        blend_forward_v3_kernel<64, true><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
-                                                                                  im.final_T, pv, out_color);
-    else
+    } else {
+        // feature rows that are not 16-byte aligned slices (C % 4 != 0) cannot be bulk-copied: plain loads
         blend_forward_v3_kernel<64, false><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,
                                                                                    im.final_T, pv, out_color);
-    SGB_LAUNCH_CHECK("blend_forward_v3_kernel", in.debug, s);
+    }
+    SGB_LAUNCH_CHECK("blend_forward kernel", in.debug, s);
     return SGB_OK;
 }
 
@@ -1474,59 +955,32 @@ int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVi
     const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
     const int chunks = (in.C + 63) / 64;
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
-    const size_t smem = sizeof(float) * 8 * kSeg * 32;
-    const size_t smem_g = smem + sizeof(float) * (2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
+    const size_t smem_g = sizeof(float) * (8 * kSeg * 32 + 2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
     const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
     static bool attr_set = false;
     if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(chain_backward_v3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SGB_CUDA(cudaFuncSetAttribute(chain_backward_v3_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
         attr_set = true;
     }
-    const char* dbg = getenv("SGB_BWD_DIRECT");  // diagnostics: 1 = shuffle-reduce kernels instead of the GEMM-shaped ones
-    const bool rows16 = (in.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(dL_dpix) & 15) == 0);
-    if (!dbg && rows16) {
-        {
-            StageTimer t(ctx, ST_BLEND_BWD, s);
-            ctx->launches += 1;
-            if (vec)
-                chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                                im.final_T, dL_dpix, pv, dL_dmean2D,
-                                                                                dL_dconic, dL_dopacity);
-            else
-                chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                                 im.final_T, dL_dpix, pv, dL_dmean2D,
-                                                                                 dL_dconic, dL_dopacity);
-            SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
-        }
-        StageTimer t(ctx, ST_DFEATURE, s);
-        ctx->launches += 1;
-        dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
-        SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
-        return SGB_OK;
-    }
     {
         StageTimer t(ctx, ST_BLEND_BWD, s);
         ctx->launches += 1;
         if (vec)
-            chain_backward_v3_kernel<64, true><<<tiles, kThreads, smem, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+            chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
                                                                             im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
                                                                             dL_dopacity);
         else
-            chain_backward_v3_kernel<64, false><<<tiles, kThreads, smem, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+            chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
                                                                              im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
                                                                              dL_dopacity);
-        SGB_LAUNCH_CHECK("chain_backward_v3_kernel", in.debug, s);
+        SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
     }
-    {
-        StageTimer t(ctx, ST_DFEATURE, s);
-        ctx->launches += 1;
-        dfeature_v3_kernel<64><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
-        SGB_LAUNCH_CHECK("dfeature_v3_kernel", in.debug, s);
-    }
+    StageTimer t(ctx, ST_DFEATURE, s);
+    ctx->launches += 1;
+    dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
+    SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
     return SGB_OK;
 }
 
