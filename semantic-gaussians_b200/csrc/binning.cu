@@ -34,11 +34,12 @@ __global__ void gather_counts_kernel(int P, const uint32_t* __restrict__ perm,
 // One warp handles 32 consecutive slots of the depth order; for each visible Gaussian its lanes
 // write the tile keys / ids of its rectangle cooperatively (coalesced), instead of one thread
 // walking the whole rectangle (duplicateWithKeys, rasterizer_impl.cu:70-111).
+template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ perm,
                                                              const uint32_t* __restrict__ offsets,
                                                              const SplatRec* __restrict__ rec,
                                                              const int* __restrict__ radii, dim3 grid,
-                                                             uint32_t* __restrict__ keys,
+                                                             KeyT* __restrict__ keys,
                                                              uint32_t* __restrict__ vals) {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -68,27 +69,32 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
         uint32_t ww = __shfl_sync(0xffffffffu, w, src);
         for (uint32_t k = lane; k < nn; k += 32) {
             uint32_t ty = k / ww, tx = k - ty * ww;
-            keys[o + k] = (yy + ty) * grid.x + (xx + tx);  // key = y*grid.x + x, rasterizer_impl.cu:102
+            keys[o + k] = (KeyT)((yy + ty) * grid.x + (xx + tx));  // key = y*grid.x + x, rasterizer_impl.cu:102
             vals[o + k] = g;
         }
     }
 }
 
-// rasterizer_impl.cu:116-138 on 32-bit tile keys.
-__global__ void identify_ranges_kernel(int64_t L, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    uint32_t cur = keys[idx];
-    if (idx == 0)
-        ranges[cur].x = 0;
-    else {
-        uint32_t prev = keys[idx - 1];
-        if (cur != prev) {
-            ranges[prev].y = (uint32_t)idx;
-            ranges[cur].x = (uint32_t)idx;
+// Tile ranges of the sorted instance list: same result as identifyTileRanges
+// (rasterizer_impl.cu:116-138 — {start, end} of every tile that owns instances, {0, 0} otherwise),
+// computed by one thread per TILE with two binary searches instead of one thread per instance
+// re-reading the whole key array (R = 45 M keys on K2/K3).
+template <typename KeyT>
+__global__ void tile_ranges_kernel(int64_t L, uint32_t tiles, const KeyT* __restrict__ keys,
+                                   uint2* __restrict__ ranges) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tiles) return;
+    auto lower = [&](uint32_t v) {  // first index with key >= v
+        int64_t lo = 0, hi = L;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((uint32_t)keys[mid] < v) lo = mid + 1;
+            else hi = mid;
         }
-    }
-    if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+        return lo;
+    };
+    const int64_t a = lower(t), b = lower(t + 1);
+    ranges[t] = (b > a) ? make_uint2((uint32_t)a, (uint32_t)b) : make_uint2(0u, 0u);
 }
 
 // rasterizer_impl.cu:35-50
@@ -177,33 +183,26 @@ int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g
     return SGB_OK;
 }
 
-int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                const int32_t* radii, cudaStream_t s) {
-    dim3 tile_grid((in.W + SGB_TILE - 1) / SGB_TILE, (in.H + SGB_TILE - 1) / SGB_TILE, 1);
-    const size_t tiles = (size_t)tile_grid.x * tile_grid.y;
-    SGB_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), s));  // rasterizer_impl.cu:313
-    if (R == 0) return SGB_OK;
-    if (ctx->last_P != in.P || !ctx->d_perm) {
-        set_error("sgb_forward_render called without a matching sgb_forward_geometry on this ctx");
-        return SGB_E_INVALID;
-    }
+template <typename KeyT>
+static int run_binning_t(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                         const int32_t* radii, dim3 tile_grid, cudaStream_t s) {
+    const uint32_t tiles = tile_grid.x * tile_grid.y;
     size_t sort_tmp = 0;
-    const int bits = (int)higher_msb((uint32_t)tiles);
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+    const int bits = (int)higher_msb(tiles);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (KeyT*)nullptr, (KeyT*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, R, 0, bits, s);
-    size_t arr = align_up(sizeof(uint32_t) * (size_t)R);
-    int rc = ctx->bin.ensure(3 * arr + align_up(sort_tmp));
+    const size_t karr = align_up(sizeof(KeyT) * (size_t)R), varr = align_up(sizeof(uint32_t) * (size_t)R);
+    int rc = ctx->bin.ensure(2 * karr + varr + align_up(sort_tmp));
     if (rc) return rc;
     char* base = (char*)ctx->bin.p;
-    uint32_t* keys_unsorted = (uint32_t*)base;
-    uint32_t* keys_sorted = (uint32_t*)(base + arr);
-    uint32_t* vals_unsorted = (uint32_t*)(base + 2 * arr);
-    void* cub_tmp = base + 3 * arr;
-
+    KeyT* keys_unsorted = (KeyT*)base;
+    KeyT* keys_sorted = (KeyT*)(base + karr);
+    uint32_t* vals_unsorted = (uint32_t*)(base + 2 * karr);
+    void* cub_tmp = base + 2 * karr + varr;
     {
         StageTimer t(ctx, ST_EMIT, s);
-        emit_instances_kernel<<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
-                                                                tile_grid, keys_unsorted, vals_unsorted);
+        emit_instances_kernel<KeyT><<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
+                                                                      tile_grid, keys_unsorted, vals_unsorted);
         SGB_LAUNCH_CHECK("emit_instances_kernel", in.debug, s);
         ctx->launches += 1;
     }
@@ -215,11 +214,28 @@ int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, 
     }
     {
         StageTimer t(ctx, ST_RANGES, s);
-        identify_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, im.ranges);
-        SGB_LAUNCH_CHECK("identify_ranges_kernel", in.debug, s);
+        tile_ranges_kernel<KeyT><<<(tiles + 127) / 128, 128, 0, s>>>(R, tiles, keys_sorted, im.ranges);
+        SGB_LAUNCH_CHECK("tile_ranges_kernel", in.debug, s);
         ctx->launches += 1;
     }
     return SGB_OK;
+}
+
+int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                const int32_t* radii, cudaStream_t s) {
+    dim3 tile_grid((in.W + SGB_TILE - 1) / SGB_TILE, (in.H + SGB_TILE - 1) / SGB_TILE, 1);
+    const size_t tiles = (size_t)tile_grid.x * tile_grid.y;
+    if (R == 0) {
+        SGB_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), s));  // rasterizer_impl.cu:313
+        return SGB_OK;
+    }
+    if (ctx->last_P != in.P || !ctx->d_perm) {
+        set_error("sgb_forward_render called without a matching sgb_forward_geometry on this ctx");
+        return SGB_E_INVALID;
+    }
+    // 16-bit tile keys halve the key traffic of the R-sized sort whenever the tile count allows it
+    if (tiles <= 0xFFFFu) return run_binning_t<uint16_t>(ctx, in, R, g, b, im, radii, tile_grid, s);
+    return run_binning_t<uint32_t>(ctx, in, R, g, b, im, radii, tile_grid, s);
 }
 
 }  // namespace sgb
