@@ -111,6 +111,12 @@ const char* sgb_profile_stage_name(int stage);
 /* Kernels of this library launched through ctx so far (library_calls = 0), or the number of
  * CUB device-wide calls (library_calls = 1; each is several kernels). */
 uint64_t sgb_ctx_launch_count(const sgb_ctx* ctx, int library_calls);
+/* Optional cudaEvent_t that sgb_backward records on its stream as soon as dL_dcolors (the (P, C)
+ * feature gradient — the only large per-Gaussian gradient) is final, i.e. BEFORE the chain and
+ * geometry gradient kernels.  A data-parallel caller lets its communication stream wait on this
+ * event so that the all-reduce of the feature gradient overlaps the rest of the backward pass
+ * (the reference is single-GPU and has no counterpart).  NULL (default) disables it. */
+int sgb_ctx_set_feature_grad_event(sgb_ctx* ctx, void* cuda_event);
 
 /* Sizes of the three caller-owned state buffers (multiples of 256 B). */
 size_t sgb_geometry_bytes(int32_t P);
@@ -190,6 +196,27 @@ int sgb_fusion_accumulate(sgb_ctx* ctx, const sgb_fusion_view* v, const void* fe
 
 /* fusion.py:146-147: count[count==0] = 1e-5; feat_sum /= count (in place). */
 int sgb_fusion_normalize(int32_t P, int32_t C, float* feat_sum, float* count, void* stream);
+
+/* ---- semantic head: what every render_chn caller runs on the rendered feature image.
+ *
+ * sgb_semantic_head: render (C, N) planar fp32 with N = H*W, text (K, C) row-major:
+ *     sim[k][p]  = sum_c text[k][c] * render[c][p] / (||render[:, p]||_2 + 1e-8)   eval_segmentation.py:155-156
+ *     label[p]   = argmax_{k >= first_class} sim[k][p] - first_class                eval_segmentation.py:157
+ * in ONE pass over the image.  sim (K, N) and label (N, int64) are optional (NULL to skip; a label-only
+ * call never writes the K planes).  ctx is needed only for K > 32 with a label map (scratch), else may be NULL.
+ *
+ * sgb_feature_logits: out[p][k] = sum_c features[p][c] * text[k][c]  (einsum "cq,dq->dc",
+ * eval_segmentation.py:132, view_viser.py:185) with row pitch Kpad >= K, columns K..Kpad-1 zeroed — blending is
+ * linear, so rendering these Kpad channels gives the un-normalised similarities (and hence the label map)
+ * without ever materialising the (C, H, W) feature image.
+ *
+ * sgb_label_argmax: label[p] = argmax_{first_class <= k < K} planes[k][p] - first_class
+ * (rendering[1:].argmax(dim=0), eval_segmentation.py:144). */
+int sgb_semantic_head(sgb_ctx* ctx, int32_t C, int32_t K, int64_t N, const float* render, const float* text,
+                      int32_t first_class, float* sim, int64_t* label, void* stream);
+int sgb_feature_logits(int32_t P, int32_t C, int32_t K, int32_t Kpad, const float* features, const float* text,
+                       float* out, void* stream);
+int sgb_label_argmax(int32_t K, int32_t first_class, int64_t N, const float* planes, int64_t* label, void* stream);
 
 #ifdef __cplusplus
 }

@@ -210,7 +210,10 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
     int rc = check_inputs(in);
     if (rc) return rc;
     if (!ctx || !gr || !dL_dpix || !image_state) { set_error("sgb_backward: null argument"); return SGB_E_INVALID; }
-    if (in->P == 0) return SGB_OK;
+    if (in->P == 0) {
+        if (ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
+        return SGB_OK;
+    }
     if (!geometry_state || !radii || !gr->dL_dmeans2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolors ||
         !gr->dL_dmeans3D || !gr->dL_dcov3D || (in->shs && !gr->dL_dsh) || (in->scales && (!gr->dL_dscales || !gr->dL_drotations))) {
         set_error("sgb_backward: null state or gradient buffer");
@@ -231,10 +234,19 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
                                    gr->dL_dcolors, s);
         if (rc) return rc;
     }
+    // C > 4 records the event inside blend_backward_v3, right after the dL/dfeature kernel
+    if (ctx->feature_grad_event && !(num_rendered > 0 && in->C > 4))
+        SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
     const float* cov3D = in->cov3D_precomp ? in->cov3D_precomp : g.cov3D;  // rasterizer_impl.cu:417
     StageTimer t(ctx, ST_GEOM_BWD, s);
     ctx->launches += 1;
     return launch_geom_backward(*in, g, radii, cov3D, gr->dL_dcolors, *gr, s);
+}
+
+int sgb_ctx_set_feature_grad_event(sgb_ctx* ctx, void* cuda_event) {
+    if (!ctx) { set_error("sgb_ctx_set_feature_grad_event: null ctx"); return SGB_E_INVALID; }
+    ctx->feature_grad_event = (cudaEvent_t)cuda_event;
+    return SGB_OK;
 }
 
 int sgb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

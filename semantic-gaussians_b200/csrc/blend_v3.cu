@@ -327,18 +327,7 @@ constexpr int kSeg = 64;  // entries per backward segment (4 chunks); S[8 warps]
 //     dfeature  dF[G][64 ch]        = W[G][256 px]    . dL[256 px][64]   K = 256 px lane tile 4 entries x 8 ch
 // Register tiles make every product 64-128 FMAs per 4-6 shared-memory loads and need no cross-lane
 // reductions (an earlier shuffle-reduce formulation spent ~40 % of its issue slots on SHFL/FSEL/FADD).
-constexpr int kEB = 64;  // entries per staged batch
-
-// Sequential reader of a tile's entry list for whole-CTA staging: thread t < cnt gets entry base+t.
-struct BatchCursor {
-    uint32_t n, done, c0;  // entries, entries already handed out, chunk holding entry `done`
-    __device__ __forceinline__ void init(const PoolView& pool, int tile) {
-        n = pool.count[tile];
-        done = 0;
-        c0 = pool.head[tile];
-    }
-};
-// chunk index holding entry (done + k): walks `next` pointers (k / 16 hops, at most 4)
+// chunk index holding the entry k places after the first entry of chunk c0: walks `next` pointers (k / 16 hops)
 __device__ __forceinline__ uint32_t chunk_at(const PoolView& pool, uint32_t c0, int k) {
     uint32_t c = min(c0, pool.capacity - 1);
     for (int h = k / kChunkEntries; h > 0; h--) c = min(pool.chunks[c].next, pool.capacity - 1);
@@ -964,6 +953,15 @@ int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVi
         SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
         attr_set = true;
     }
+    // dL/dfeature first: it needs only the weight rows and dL/dout, and it is the one large
+    // gradient, so a data-parallel caller can start reducing it while the chain runs (sgb200.h)
+    {
+        StageTimer t(ctx, ST_DFEATURE, s);
+        ctx->launches += 1;
+        dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
+        SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
+    }
+    if (ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
     {
         StageTimer t(ctx, ST_BLEND_BWD, s);
         ctx->launches += 1;
@@ -977,10 +975,6 @@ int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVi
                                                                              dL_dopacity);
         SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
     }
-    StageTimer t(ctx, ST_DFEATURE, s);
-    ctx->launches += 1;
-    dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
-    SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
     return SGB_OK;
 }
 

@@ -1,0 +1,327 @@
+// Open-vocabulary semantic head that every render_chn caller of the reference runs right after the
+// rasterizer:
+//
+//   rendering = rendering / (rendering.norm(dim=0, keepdim=True) + 1e-8)      eval_segmentation.py:155,255,396
+//   sim       = torch.einsum("cq,qhw->chw", text_features, rendering)         eval_segmentation.py:156,256,397
+//   label     = sim[1:].argmax(dim=0)                                         eval_segmentation.py:157,257,398
+//
+// and its per-Gaussian twin  sim = einsum("cq,dq->dc", text_features, features)  (eval_segmentation.py:132,232;
+// view_viser.py:185,217).  In torch that is four passes over the (C,H,W) image (norm, divide, einsum,
+// arg-max: ~4x 2.1 GB at K3 sizes); here the image is read ONCE: every thread owns four pixels, walks
+// the channel planes with 16-byte loads and keeps K running dot products plus the squared norm in
+// registers; the class embeddings sit transposed in shared memory and are read as broadcasts.
+#include "common.cuh"
+
+namespace sgb {
+
+namespace {
+
+constexpr int kHeadThreads = 256;
+constexpr int kHeadPix = 4;       // pixels per thread
+constexpr int kHeadSlab = 128;    // channels of the class embeddings staged per shared-memory slab
+constexpr int kMaxKC = 32;        // classes per pass (one register accumulator per class and pixel)
+
+// NK4 = (classes per pass) / 4.  VEC: the N-float planes are 16-byte aligned (N % 4 == 0): pixel
+// group = 4 consecutive pixels, one LDG.128 per channel; otherwise the thread's 4 pixels are strided
+// by the block width and loaded as scalars (still coalesced across the warp).
+template <int NK4, bool VEC>
+__global__ void __launch_bounds__(kHeadThreads) semantic_head_kernel(
+    int C, int K, long long N, const float* __restrict__ render, const float* __restrict__ text, int first_class,
+    float* __restrict__ sim, long long* __restrict__ label, float* __restrict__ best_val, int k0, int multi) {
+    constexpr int KC = NK4 * 4;
+    __shared__ __align__(16) float Ts[kHeadSlab][KC];  // [channel][class], zero padded
+    const int tid = threadIdx.x;
+    // k0: first class of this pass; multi: 0 = the only pass, 1 = first of several, 2 = a later pass
+    const int kc = min(KC, K - k0);
+    const long long blk = (long long)blockIdx.x * (kHeadThreads * kHeadPix);
+    long long px[kHeadPix];
+#pragma unroll
+    for (int i = 0; i < kHeadPix; i++) px[i] = VEC ? blk + (long long)tid * kHeadPix + i : blk + (long long)i * kHeadThreads + tid;
+    // VEC: N % 4 == 0, so a group of four pixels is inside the image as soon as its first pixel is
+    const bool any = px[0] < N;
+
+    float2 acc[kHeadPix / 2][KC];  // [pixel pair][class]
+#pragma unroll
+    for (int p = 0; p < kHeadPix / 2; p++)
+#pragma unroll
+        for (int k = 0; k < KC; k++) acc[p][k] = make_float2(0.f, 0.f);
+    float2 nrm[kHeadPix / 2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+
+    for (int c0 = 0; c0 < C; c0 += kHeadSlab) {
+        const int cs = min(kHeadSlab, C - c0);
+        __syncthreads();
+        for (int e = tid; e < kHeadSlab * KC; e += kHeadThreads) {
+            const int c = e / KC, k = e - c * KC;
+            Ts[c][k] = (c < cs && k < kc) ? __ldg(text + (size_t)(k0 + k) * C + c0 + c) : 0.f;
+        }
+        __syncthreads();
+        if (!any) continue;
+        const float* src = render + (size_t)c0 * N;
+#pragma unroll 4
+        for (int c = 0; c < cs; c++) {
+            float x[kHeadPix];
+            if (VEC) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * N + px[0]));
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < kHeadPix; i++) x[i] = px[i] < N ? __ldg(src + (size_t)c * N + px[i]) : 0.f;
+            }
+            const float2 x01 = make_float2(x[0], x[1]), x23 = make_float2(x[2], x[3]);
+            nrm[0] = ffma2(x01, x01, nrm[0]);
+            nrm[1] = ffma2(x23, x23, nrm[1]);
+#pragma unroll
+            for (int q = 0; q < NK4; q++) {
+                const float4 t = *reinterpret_cast<const float4*>(&Ts[c][q * 4]);
+                const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 t2 = make_float2(tt[j], tt[j]);
+                    acc[0][q * 4 + j] = ffma2(x01, t2, acc[0][q * 4 + j]);
+                    acc[1][q * 4 + j] = ffma2(x23, t2, acc[1][q * 4 + j]);
+                }
+            }
+        }
+    }
+    if (!any) return;
+
+    // sim = dot / (||x|| + 1e-8)
+    float inv[kHeadPix];
+    inv[0] = 1.f / (sqrtf(nrm[0].x) + 1e-8f);
+    inv[1] = 1.f / (sqrtf(nrm[0].y) + 1e-8f);
+    inv[2] = 1.f / (sqrtf(nrm[1].x) + 1e-8f);
+    inv[3] = 1.f / (sqrtf(nrm[1].y) + 1e-8f);
+    float bv[kHeadPix];
+    int bk[kHeadPix];
+#pragma unroll
+    for (int i = 0; i < kHeadPix; i++) { bv[i] = 0.f; bk[i] = -1; }
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+        if (k >= kc) break;
+        float s[kHeadPix] = {acc[0][k].x * inv[0], acc[0][k].y * inv[1], acc[1][k].x * inv[2], acc[1][k].y * inv[3]};
+        if (sim) {
+            float* dst = sim + (size_t)(k0 + k) * N;
+            if (VEC) *reinterpret_cast<float4*>(dst + px[0]) = make_float4(s[0], s[1], s[2], s[3]);
+            else {
+#pragma unroll
+                for (int i = 0; i < kHeadPix; i++) if (px[i] < N) dst[px[i]] = s[i];
+            }
+        }
+        if (k0 + k >= first_class) {
+#pragma unroll
+            for (int i = 0; i < kHeadPix; i++)
+                if (bk[i] < 0 || s[i] > bv[i]) { bv[i] = s[i]; bk[i] = k0 + k; }  // first maximum wins, like torch.argmax
+        }
+    }
+    if (label) {
+#pragma unroll
+        for (int i = 0; i < kHeadPix; i++) {
+            if (px[i] >= N || bk[i] < 0) continue;
+            if (multi == 0) {
+                label[px[i]] = (long long)(bk[i] - first_class);
+            } else {
+                // more than 32 classes: the passes are separate launches, one after another on the
+                // stream, and keep the running maximum in best_val (strictly greater: first maximum wins)
+                if (multi == 1 || bv[i] > best_val[px[i]]) {
+                    best_val[px[i]] = bv[i];
+                    label[px[i]] = (long long)(bk[i] - first_class);
+                }
+            }
+        }
+    }
+}
+
+// Per-Gaussian similarities  out[p][k] = sum_c features[p][c] * text[k][c]  (einsum "cq,dq->dc"),
+// written with a row pitch of Kpad floats, columns K..Kpad-1 zero.  One warp per Gaussian row:
+// lanes stride over the channels (coalesced 512-byte pieces), class embeddings in shared memory.
+template <int KC>
+__global__ void __launch_bounds__(256) feature_logits_kernel(int P, int C, int K, int Kpad, int k0,
+                                                             const float* __restrict__ features,
+                                                             const float* __restrict__ text, float* __restrict__ out) {
+    extern __shared__ __align__(16) float Tk[];  // [KC][Cp], Cp = C rounded up to 4, zero padded
+    const int Cp = (C + 3) & ~3;
+    const int kc = min(KC, K - k0);
+    for (int e = threadIdx.x; e < KC * Cp; e += blockDim.x) {
+        const int k = e / Cp, c = e - k * Cp;
+        Tk[e] = (k < kc && c < C) ? __ldg(text + (size_t)(k0 + k) * C + c) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const bool vec = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(features) & 15) == 0);
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
+        float acc[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) acc[k] = 0.f;
+        const float* row = features + (size_t)p * C;
+        for (int c = lane * 4; c < Cp; c += 128) {
+            float4 f;
+            if (vec) f = __ldg(reinterpret_cast<const float4*>(row + c));
+            else {
+                f.x = c < C ? __ldg(row + c) : 0.f;
+                f.y = c + 1 < C ? __ldg(row + c + 1) : 0.f;
+                f.z = c + 2 < C ? __ldg(row + c + 2) : 0.f;
+                f.w = c + 3 < C ? __ldg(row + c + 3) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                const float4 t = *reinterpret_cast<const float4*>(&Tk[k * Cp + c]);
+                acc[k] = fmaf(f.x, t.x, acc[k]);
+                acc[k] = fmaf(f.y, t.y, acc[k]);
+                acc[k] = fmaf(f.z, t.z, acc[k]);
+                acc[k] = fmaf(f.w, t.w, acc[k]);
+            }
+        }
+        // transpose-reduce: after the butterfly every lane holds all sums; lane k stores class k
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            float v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == k) mine = v;
+        }
+        if (lane < KC && k0 + lane < Kpad) out[(size_t)p * Kpad + k0 + lane] = lane < kc ? mine : 0.f;  // pad columns = 0
+    }
+}
+
+// label[p] = argmax_{k in [first_class, K)} planes[k][p] - first_class   (rendering[1:].argmax(dim=0),
+// eval_segmentation.py:144,244,375,418)
+__global__ void label_argmax_kernel(int K, int first_class, long long N, const float* __restrict__ planes,
+                                    long long* __restrict__ label) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    float bv = __ldg(planes + (size_t)first_class * N + p);
+    int bk = first_class;
+    for (int k = first_class + 1; k < K; k++) {
+        const float v = __ldg(planes + (size_t)k * N + p);
+        if (v > bv) { bv = v; bk = k; }
+    }
+    label[p] = (long long)(bk - first_class);
+}
+
+template <int NK4>
+void launch_head_t(int C, int K, long long N, const float* render, const float* text, int first_class, float* sim,
+                   long long* label, float* best_val, int k0, int multi, cudaStream_t s) {
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(render) & 15) == 0) &&
+                     (!sim || (reinterpret_cast<uintptr_t>(sim) & 15) == 0);
+    const unsigned blocks = (unsigned)((N + kHeadThreads * kHeadPix - 1) / (kHeadThreads * kHeadPix));
+    if (vec)
+        semantic_head_kernel<NK4, true><<<blocks, kHeadThreads, 0, s>>>(C, K, N, render, text, first_class, sim, label,
+                                                                       best_val, k0, multi);
+    else
+        semantic_head_kernel<NK4, false><<<blocks, kHeadThreads, 0, s>>>(C, K, N, render, text, first_class, sim, label,
+                                                                        best_val, k0, multi);
+}
+
+}  // namespace
+
+static int launch_semantic_head(sgb_ctx* ctx, int C, int K, long long N, const float* render, const float* text,
+                         int first_class, float* sim, long long* label, cudaStream_t s) {
+    const int passes = (K + kMaxKC - 1) / kMaxKC;
+    float* best_val = nullptr;
+    if (passes > 1 && label) {
+        if (!ctx) { set_error("sgb_semantic_head: more than %d classes with a label map needs a ctx (scratch)", kMaxKC); return SGB_E_INVALID; }
+        int rc = ctx->misc.ensure(sizeof(float) * (size_t)N);
+        if (rc) return rc;
+        best_val = (float*)ctx->misc.p;
+    }
+    for (int pass = 0; pass < passes; pass++) {
+        const int k0 = pass * kMaxKC;
+        const int kc = min(kMaxKC, K - k0);
+        // a pass entirely below first_class still writes its sim planes but takes no part in the arg-max;
+        // the first pass that does initialises best_val
+        const int multi = passes == 1 ? 0 : (pass == first_class / kMaxKC ? 1 : 2);
+        long long* lab = (k0 + kc <= first_class) ? nullptr : label;
+        if (!sim && !lab) continue;
+        const int nk4 = (kc + 3) / 4;
+        if (nk4 <= 2) launch_head_t<2>(C, K, N, render, text, first_class, sim, lab, best_val, k0, multi, s);
+        else if (nk4 <= 4) launch_head_t<4>(C, K, N, render, text, first_class, sim, lab, best_val, k0, multi, s);
+        else if (nk4 <= 6) launch_head_t<6>(C, K, N, render, text, first_class, sim, lab, best_val, k0, multi, s);
+        else launch_head_t<8>(C, K, N, render, text, first_class, sim, lab, best_val, k0, multi, s);
+        SGB_LAUNCH_CHECK("semantic_head_kernel", 0, s);
+        if (ctx) ctx->launches += 1;
+    }
+    return SGB_OK;
+}
+
+template <int KC>
+static int launch_logits_t(int P, int C, int K, int Kpad, int k0, const float* features, const float* text, float* out,
+                           cudaStream_t s) {
+    const int Cp = (C + 3) & ~3;
+    const size_t smem = sizeof(float) * (size_t)KC * Cp;
+    if (smem > 200 * 1024) {
+        set_error("sgb_feature_logits: C = %d too large (class embeddings must fit shared memory)", C);
+        return SGB_E_INVALID;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(feature_logits_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const int blocks = min((P + 7) / 8, 148 * 4);
+    feature_logits_kernel<KC><<<blocks, 256, smem, s>>>(P, C, K, Kpad, k0, features, text, out);
+    SGB_LAUNCH_CHECK("feature_logits_kernel", 0, s);
+    return SGB_OK;
+}
+
+static int launch_feature_logits(int P, int C, int K, int Kpad, const float* features, const float* text, float* out,
+                          cudaStream_t s) {
+    for (int k0 = 0; k0 < Kpad; k0 += 32) {
+        const int span = min(32, Kpad - k0);  // columns this pass writes (classes + zero padding)
+        int rc;
+        if (span <= 8) rc = launch_logits_t<8>(P, C, K, Kpad, k0, features, text, out, s);
+        else if (span <= 16) rc = launch_logits_t<16>(P, C, K, Kpad, k0, features, text, out, s);
+        else if (span <= 24) rc = launch_logits_t<24>(P, C, K, Kpad, k0, features, text, out, s);
+        else rc = launch_logits_t<32>(P, C, K, Kpad, k0, features, text, out, s);
+        if (rc) return rc;
+    }
+    return SGB_OK;
+}
+
+static int launch_label_argmax(int K, int first_class, long long N, const float* planes, long long* label, cudaStream_t s) {
+    label_argmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(K, first_class, N, planes, label);
+    SGB_LAUNCH_CHECK("label_argmax_kernel", 0, s);
+    return SGB_OK;
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" {
+
+int sgb_semantic_head(sgb_ctx* ctx, int32_t C, int32_t K, int64_t N, const float* render, const float* text,
+                      int32_t first_class, float* sim, int64_t* label, void* stream) {
+    if (C <= 0 || K <= 0 || N < 0 || first_class < 0 || first_class >= K) {
+        set_error("sgb_semantic_head: need C > 0, K > 0, N >= 0 and 0 <= first_class < K");
+        return SGB_E_INVALID;
+    }
+    if (N == 0 || (!sim && !label)) return SGB_OK;
+    if (!render || !text) { set_error("sgb_semantic_head: null input"); return SGB_E_INVALID; }
+    return launch_semantic_head(ctx, C, K, (long long)N, render, text, first_class, sim, (long long*)label,
+                                (cudaStream_t)stream);
+}
+
+int sgb_feature_logits(int32_t P, int32_t C, int32_t K, int32_t Kpad, const float* features, const float* text,
+                       float* out, void* stream) {
+    if (P < 0 || C <= 0 || K <= 0 || Kpad < K) {
+        set_error("sgb_feature_logits: need P >= 0, C > 0, K > 0, Kpad >= K");
+        return SGB_E_INVALID;
+    }
+    if (P == 0) return SGB_OK;
+    if (!features || !text || !out) { set_error("sgb_feature_logits: null argument"); return SGB_E_INVALID; }
+    return launch_feature_logits(P, C, K, Kpad, features, text, out, (cudaStream_t)stream);
+}
+
+int sgb_label_argmax(int32_t K, int32_t first_class, int64_t N, const float* planes, int64_t* label, void* stream) {
+    if (K <= 0 || first_class < 0 || first_class >= K || N < 0) {
+        set_error("sgb_label_argmax: need K > 0, 0 <= first_class < K, N >= 0");
+        return SGB_E_INVALID;
+    }
+    if (N == 0) return SGB_OK;
+    if (!planes || !label) { set_error("sgb_label_argmax: null argument"); return SGB_E_INVALID; }
+    return launch_label_argmax(K, first_class, (long long)N, planes, (long long*)label, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -63,6 +63,58 @@ def allreduce_sums(tensors: Sequence[torch.Tensor], group=None, bucket_bytes: in
         w.wait()
 
 
+def nccl_overlap_options():
+    """Process-group options for ``dist.init_process_group("nccl", pg_options=...)``: NCCL's stream gets high
+    priority.  The chain-backward kernel fills every SM for ~5 ms in 27 waves; at equal priority the block
+    scheduler keeps handing freed SM slots to ITS pending CTAs, so an all-reduce launched meanwhile only
+    starts in the last wave (measured: no overlap at all).  With a high-priority stream the NCCL CTAs are
+    placed as soon as the first chain CTAs retire (~0.2 ms)."""
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
+class OverlappedFeatureGradReduce:
+    """All-reduce of the (P, C) feature gradient overlapped with the rest of the backward pass.
+
+    sgb_backward computes dL/dfeature FIRST and records a CUDA event when it is final
+    (sgb_ctx_set_feature_grad_event, include/sgb200.h); the chain / geometry gradient kernels that follow
+    only touch small tensors.  `start(grad)` — called right after `.backward()` returned on the host,
+    while the GPU is still working through those kernels — makes a communication stream wait on that
+    event only and launches the NCCL sum there; `finish()` joins it back into the current stream.
+    One view per rank per exchange (autograd adds a second view's gradient after the event).
+    Create the process group with ``nccl_overlap_options()`` or the overlap will not materialise."""
+
+    def __init__(self, device: torch.device, group=None):
+        from . import _lib
+        self.device, self.group = torch.device(device), group
+        self.comm_stream = torch.cuda.Stream(self.device, priority=-1)
+        self.event = torch.cuda.Event()
+        cur = torch.cuda.current_stream(self.device)
+        self.event.record(cur)                      # materialises the cudaEvent_t
+        self._ctx = _lib.ctx_for(self.device.index, cur.cuda_stream)
+        _lib.set_feature_grad_event(self._ctx, self.event.cuda_event)
+        self._work = None
+
+    def start(self, feature_grad: torch.Tensor) -> None:
+        if not feature_grad.is_contiguous():
+            raise ValueError("feature gradient must be contiguous (reduced in place)")
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self.event)
+            self._work = dist.all_reduce(feature_grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+
+    def close(self) -> None:
+        from . import _lib
+        self.finish()
+        _lib.set_feature_grad_event(self._ctx, None)
+
+
 def render_views_sharded(views: Sequence, render_fn, loss_fn, params: Iterable[torch.Tensor], group=None,
                          rank: Optional[int] = None, world: Optional[int] = None):
     """Forward + backward of this rank's shard of a view batch, gradients accumulated over the local

@@ -36,6 +36,30 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    from semantic_gaussians_b200.distributed import nccl_overlap_options
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=nccl_overlap_options())
+    try:
+        from semantic_gaussians_b200 import distributed as D
+        ov = D.OverlappedFeatureGradReduce(dev)
+        outs = []
+        for rep in range(3):                       # the event is re-recorded by every backward
+            g = _grads(dev, [rank])                # one view per rank, then the overlapped exchange
+            ov.start(g[0])
+            D.allreduce_sums(g[1:])
+            ov.finish()
+            outs.append([t.cpu().numpy() for t in g])
+        ov.close()
+        q.put((rank, outs))
+    finally:
+        dist.destroy_process_group()
+
+
 def _grads(dev, view_ids):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from util import dev_cam, dev_scene, run_ours
@@ -72,3 +96,24 @@ def test_view_sharded_gradients_match_single_gpu():
         assert np.array_equal(a, b)
         scale = np.abs(s).max()
         assert np.abs(a - s).max() <= 1e-4 * scale + 1e-7
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_overlapped_feature_grad_allreduce_matches_single_gpu():
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = [t.cpu().numpy() for t in _grads(torch.device("cuda:0"), [0, 1])]
+    for rep in range(3):
+        for a, b, s in zip(res[0][1][rep], res[1][1][rep], single):
+            assert np.array_equal(a, b)
+            scale = np.abs(s).max()
+            assert np.abs(a - s).max() <= 1e-4 * scale + 1e-7
