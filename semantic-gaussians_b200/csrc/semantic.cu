@@ -131,6 +131,127 @@ __global__ void __launch_bounds__(kHeadThreads) semantic_head_kernel(
     }
 }
 
+// Same head, fed by TMA.  The register-file version above keeps only ~4 x 16 B of loads in flight per
+// thread at 8 warps/SM (146 registers) and measured 1.8 TB/s on the K3 image; here the channel planes of a
+// 1024-pixel block stream through a ring of kHNS stages x kHCS channels x 4 KB filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx), ~96 KB in flight per SM, and the math never waits on a global
+// load.  Full stages run a branch-free fully unrolled 8-channel body (the per-channel tail test and the
+// per-stage barrier bookkeeping were 35 % of the instructions with 4-channel stages).  512 threads x 2 pixels: half the accumulators per thread of the 4-pixel layout, so 16 warps per SM
+// fit the register file (the 8-warp variant ran the FMA pipe at ~45 %).
+// Requires the VEC conditions (N % 4 == 0, 16-byte aligned planes) and the transposed class embeddings of
+// one pass to fit next to the ring.
+constexpr int kHCS = 8;   // channels per stage
+constexpr int kHNS = 4;   // stages
+constexpr int kTmaThreads = 512;
+constexpr int kHeadBlockPix = kTmaThreads * 2;  // 1024
+constexpr size_t kHeadRingBytes = (size_t)kHNS * kHCS * kHeadBlockPix * sizeof(float);
+
+template <int NK4>
+__global__ void __launch_bounds__(kTmaThreads, 1) semantic_head_tma_kernel(
+    int C, int K, long long N, const float* __restrict__ render, const float* __restrict__ text, int first_class,
+    float* __restrict__ sim, long long* __restrict__ label, float* __restrict__ best_val, int k0, int multi) {
+    constexpr int KC = NK4 * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*X)[kHCS][kHeadBlockPix] = reinterpret_cast<float(*)[kHCS][kHeadBlockPix]>(smem_raw);
+    float* Ts = reinterpret_cast<float*>(smem_raw + kHeadRingBytes);  // [C][KC], zero padded
+    __shared__ uint64_t full_bar[kHNS], empty_bar[kHNS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kc = min(KC, K - k0);
+    const long long blk = (long long)blockIdx.x * kHeadBlockPix;
+    const uint32_t npx = (uint32_t)min((long long)kHeadBlockPix, N - blk);  // multiple of 4
+    const long long px0 = blk + (long long)tid * 2;
+    const bool any = px0 < N;  // N is even: both pixels of the pair are inside
+
+    if (tid == 0) {
+        for (int i = 0; i < kHNS; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kTmaThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    for (int e = tid; e < C * KC; e += kTmaThreads) {
+        const int c = e / KC, k = e - c * KC;
+        Ts[e] = k < kc ? __ldg(text + (size_t)(k0 + k) * C + c) : 0.f;
+    }
+    __syncthreads();
+
+    const int nb = (C + kHCS - 1) / kHCS;
+    int pb = 0;  // next stage-batch to issue (warp 0)
+    auto produce = [&]() {  // warp 0, converged
+        const int st = pb % kHNS;
+        const int cnt = min(kHCS, C - pb * kHCS);
+        if (pb >= kHNS) mbar_wait(&empty_bar[st], (uint32_t)(((pb / kHNS) - 1) & 1));  // all warps released it
+        if (lane < cnt)
+            bulk_g2s(&X[st][lane][0], render + (size_t)(pb * kHCS + lane) * N + blk, npx * 4u, &full_bar[st]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], (uint32_t)cnt * npx * 4u);
+        pb++;
+    };
+    if (warp == 0)
+        for (int i = 0; i < kHNS - 1 && pb < nb; i++) produce();
+
+    float2 acc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; k++) acc[k] = make_float2(0.f, 0.f);
+    float2 nrm = make_float2(0.f, 0.f);
+
+    for (int b = 0; b < nb; b++) {
+        const int st = b % kHNS;
+        const int cnt = min(kHCS, C - b * kHCS);
+        if (warp == 0 && pb < nb) produce();  // refill the stage everybody left one batch ago
+        mbar_wait(&full_bar[st], (uint32_t)((b / kHNS) & 1));
+        if (any) {
+            const float* trow0 = Ts + (size_t)(b * kHCS) * KC;
+            auto channel = [&](int c) {
+                const float2 x = *reinterpret_cast<const float2*>(&X[st][c][tid * 2]);
+                nrm = ffma2(x, x, nrm);
+                const float* trow = trow0 + c * KC;
+#pragma unroll
+                for (int q = 0; q < NK4; q++) {
+                    const float4 t = *reinterpret_cast<const float4*>(trow + q * 4);
+                    acc[q * 4 + 0] = ffma2(x, make_float2(t.x, t.x), acc[q * 4 + 0]);
+                    acc[q * 4 + 1] = ffma2(x, make_float2(t.y, t.y), acc[q * 4 + 1]);
+                    acc[q * 4 + 2] = ffma2(x, make_float2(t.z, t.z), acc[q * 4 + 2]);
+                    acc[q * 4 + 3] = ffma2(x, make_float2(t.w, t.w), acc[q * 4 + 3]);
+                }
+            };
+            if (cnt == kHCS) {
+#pragma unroll
+                for (int c = 0; c < kHCS; c++) channel(c);
+            } else {
+                for (int c = 0; c < cnt; c++) channel(c);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    if (!any) return;
+
+    const float inv0 = 1.f / (sqrtf(nrm.x) + 1e-8f), inv1 = 1.f / (sqrtf(nrm.y) + 1e-8f);
+    float bv0 = 0.f, bv1 = 0.f;
+    int bk0 = -1, bk1 = -1;
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+        if (k >= kc) break;
+        const float s0 = acc[k].x * inv0, s1 = acc[k].y * inv1;
+        if (sim) *reinterpret_cast<float2*>(sim + (size_t)(k0 + k) * N + px0) = make_float2(s0, s1);
+        if (k0 + k >= first_class) {  // first maximum wins, like torch.argmax
+            if (bk0 < 0 || s0 > bv0) { bv0 = s0; bk0 = k0 + k; }
+            if (bk1 < 0 || s1 > bv1) { bv1 = s1; bk1 = k0 + k; }
+        }
+    }
+    if (label && bk0 >= 0) {
+        long long l0 = (long long)(bk0 - first_class), l1 = (long long)(bk1 - first_class);
+        if (multi != 0) {
+            if (multi == 1 || bv0 > best_val[px0]) best_val[px0] = bv0;
+            else l0 = label[px0];
+            if (multi == 1 || bv1 > best_val[px0 + 1]) best_val[px0 + 1] = bv1;
+            else l1 = label[px0 + 1];
+        }
+        *reinterpret_cast<longlong2*>(label + px0) = make_longlong2(l0, l1);  // px0 even: 16-byte aligned
+    }
+}
+
 // Per-Gaussian similarities  out[p][k] = sum_c features[p][c] * text[k][c]  (einsum "cq,dq->dc"),
 // written with a row pitch of Kpad floats, columns K..Kpad-1 zero.  One warp per Gaussian row:
 // lanes stride over the channels (coalesced 512-byte pieces), class embeddings in shared memory.
@@ -205,7 +326,18 @@ void launch_head_t(int C, int K, long long N, const float* render, const float* 
                    long long* label, float* best_val, int k0, int multi, cudaStream_t s) {
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(render) & 15) == 0) &&
                      (!sim || (reinterpret_cast<uintptr_t>(sim) & 15) == 0);
-    const unsigned blocks = (unsigned)((N + kHeadThreads * kHeadPix - 1) / (kHeadThreads * kHeadPix));
+    const unsigned blocks = (unsigned)((N + kHeadBlockPix - 1) / kHeadBlockPix);  // 1024 pixels per CTA either way
+    const size_t smem_tma = kHeadRingBytes + sizeof(float) * (size_t)C * NK4 * 4;
+    if (vec && smem_tma <= 224 * 1024 && (!label || (reinterpret_cast<uintptr_t>(label) & 15) == 0)) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(semantic_head_tma_kernel<NK4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            attr_set = true;
+        }
+        semantic_head_tma_kernel<NK4><<<blocks, kTmaThreads, smem_tma, s>>>(C, K, N, render, text, first_class, sim,
+                                                                            label, best_val, k0, multi);
+        return;
+    }
     if (vec)
         semantic_head_kernel<NK4, true><<<blocks, kHeadThreads, 0, s>>>(C, K, N, render, text, first_class, sim, label,
                                                                        best_val, k0, multi);

@@ -94,19 +94,27 @@ def label_argmax(planes: torch.Tensor, num_classes: Optional[int] = None, first_
 
 def render_semantic_labels(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, text_features: torch.Tensor,
                            features: Optional[torch.Tensor] = None, first_class: int = 1, scaling_modifier=1.0,
-                           override_shape=None, foreground=None, world_rotate=None) -> dict:
+                           override_shape=None, foreground=None, world_rotate=None,
+                           logits: Optional[torch.Tensor] = None) -> dict:
     """Label map of one view straight from per-Gaussian features, never writing the (C,H,W) image.
 
     Equivalent (up to fp32 re-association of the per-pixel sums) to the reference sequence
     ``render_chn(..., num_channels=C, override_color=features)`` -> normalise -> einsum -> ``sim[1:].argmax``:
     sum_c text[k][c] * (sum_j w_j f_j[c] + T bg[c]) = sum_j w_j (text[k].f_j) + T (text[k].bg).
+    ``logits``: a precomputed ``feature_logits(features, text_features, pad_to=4)`` — it depends only on the
+    scene and the label set, so an evaluation loop computes it once and passes it for every view.
     Returns {"label": (H,W) int64, "logits": (K,H,W) un-normalised similarities, "radii", "visibility_filter"}."""
     from .renderer import render_chn
-    if features is None:
-        features = pc._features_semantic
     t = _check(text_features, "text_features")
     K = t.shape[0]
-    g = feature_logits(features, t, pad_to=4)                      # (P, Kpad): 16-byte rows for the blend kernels
+    if logits is not None:
+        g = _check(logits, "logits")
+        if g.ndim != 2 or g.shape[1] < K or g.shape[1] % 4:
+            raise ValueError("logits must be feature_logits(features, text_features, pad_to=4)")
+    else:
+        if features is None:
+            features = pc._features_semantic
+        g = feature_logits(features, t, pad_to=4)                  # (P, Kpad): 16-byte rows for the blend kernels
     bg = _check(bg_color, "bg_color").reshape(-1)
     bgk = torch.zeros(g.shape[1], dtype=torch.float32, device=g.device)
     bgk[:K] = t.to(g.device) @ bg.to(g.device)

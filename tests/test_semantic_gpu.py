@@ -25,6 +25,9 @@ def _case(C, K, H, W, seed):
     (16, 5, 7, 9, 1),        # ragged: H*W % 4 != 0 -> scalar pixel path
     (64, 21, 32, 48, 1),     # ScanNet-20 + "other"
     (256, 21, 60, 80, 1),
+    (256, 21, 50, 82, 1),    # last 1024-pixel block partial (4100 px)
+    (768, 21, 16, 64, 1),    # OpenSeg width
+    (768, 29, 16, 64, 1),    # ring + 32-class embedding table at the shared-memory limit
     (130, 8, 16, 20, 0),     # C not a multiple of the 128-channel slab, first_class 0
     (40, 3, 8, 8, 2),        # single candidate class
     (48, 41, 16, 16, 1),     # K > 32: two class passes
@@ -133,3 +136,6 @@ def test_logit_space_labels_match_feature_image_head():
     top2 = sim[1:].topk(2, dim=0).values
     clear = (top2[0] - top2[1]) > 1e-4
     assert bool(clear.float().mean() > 0.9) and torch.equal(out["label"][clear], label[clear])
+    from semantic_gaussians_b200.semantic import feature_logits
+    out2 = render_semantic_labels(v, pc, Pipe, bg, text, logits=feature_logits(feats, text, pad_to=4))
+    assert torch.equal(out2["label"], out["label"]) and torch.equal(out2["logits"], out["logits"])

@@ -88,8 +88,13 @@ with torch.no_grad():
     def fused(i):
         return render_semantic_labels(cams[i % 8], pc, Pipe, bg, text, features=feats)["label"]
 
-    t_ft, t_full, t_fused = timed(full_torch), timed(full), timed(fused)
+    g = feature_logits(feats, text, pad_to=4)
+
+    def fused_pre(i):
+        return render_semantic_labels(cams[i % 8], pc, Pipe, bg, text, logits=g)["label"]
+
+    t_ft, t_full, t_fused, t_pre = timed(full_torch), timed(full), timed(fused), timed(fused_pre)
     print(f"label map per view: render_chn + torch head {t_ft:.3f} ms | render_chn + sgb head {t_full:.3f} ms | "
-          f"logit-space render {t_fused:.3f} ms", flush=True)
+          f"logit-space render {t_fused:.3f} ms | with per-scene logits {t_pre:.3f} ms", flush=True)
     la, lb = full(0), fused(0)
     print("label agreement fused vs full:", float((la == lb).float().mean()), flush=True)
