@@ -7,6 +7,7 @@ geometry gradients / the view counts.  One process per GPU, torch.distributed fo
 (NCCL over NVLink on the box, gloo in the CPU tests)."""
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -71,6 +72,9 @@ def nccl_overlap_options():
     placed as soon as the first chain CTAs retire (~0.2 ms)."""
     opts = dist.ProcessGroupNCCL.Options()
     opts.is_high_priority_stream = True
+    max_ctas = int(os.environ.get("SGB_NCCL_MAX_CTAS", "0"))
+    if max_ctas > 0:  # fewer NCCL CTAs = fewer SMs taken from the overlapped chain-backward kernel
+        opts.config.max_ctas = max_ctas
     return opts
 
 

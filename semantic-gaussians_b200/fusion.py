@@ -162,3 +162,45 @@ def fuse_views(gaussians, views, feature_maps, mapper_kwargs: dict, depths=None,
                           gaussians._times.view(-1), d)
     normalize_fused(gaussians._features_semantic, gaussians._times.view(-1))
     return gaussians._features_semantic
+
+
+def fuse_scene(gaussians, views, feature_maps, pipe, background, img_dim, visibility_threshold=0.25,
+               cut_boundary=0, depth="render", depth_maps=None, every: int = 5) -> dict:
+    """fuse_one_scene (fusion.py:57-148) with every step on the device.
+
+    The reference renders the depth map on the GPU, copies it to the host, projects all Gaussians in numpy,
+    gathers the (C,h,w) feature map on the CPU and copies a (P,C) tensor back — per view (fusion.py:106-144).
+    Here ``depth="render"`` feeds the rasterizer's median-depth output straight into the fusion kernels.
+
+    depth         "render" (fusion.py:110-120) | "image" (``depth_maps[idx]``, already divided by depth_scale)
+                  | "surface" | None
+    feature_maps  sequence or callable idx -> (C,h,w) float16/float32 tensor (the 2D model's output)
+    every         the shipped loop fuses every 5th view (fusion.py:61-62)
+    Returns {"features": (P,C) fused means, "mask": (P,) bool — Gaussians seen by at least one fused view
+    (``point_ids`` of fusion.py:148), "views": number of fused views}."""
+    from .renderer import render
+    if getattr(gaussians, "_features_semantic", None) is None or gaussians._features_semantic.numel() == 0:
+        raise ValueError("call gaussians.create_semantic(C) first (fusion.py:52)")
+    dev = gaussians._xyz.device
+    count = gaussians._times.view(-1)
+    fused = 0
+    with torch.no_grad():
+        for idx, view in enumerate(views):
+            if idx % every != 0:
+                continue
+            K = view.intrinsics() if callable(getattr(view, "intrinsics", None)) else view.intrinsics
+            mapper = PointCloudToImageMapper(img_dim, visibility_threshold, cut_boundary, K, device=dev)
+            fm = feature_maps(idx) if callable(feature_maps) else feature_maps[idx]
+            if depth == "render":
+                d = render(view, gaussians, pipe, background, override_shape=img_dim)["depth"][0]
+            elif depth == "image":
+                d = depth_maps[idx]
+            elif depth == "surface":
+                d = "surface"
+            else:
+                d = None
+            mapper.accumulate(view.world_view_transform, gaussians._xyz, fm, gaussians._features_semantic, count, d)
+            fused += 1
+        mask = count > 0
+        normalize_fused(gaussians._features_semantic, count)
+    return {"features": gaussians._features_semantic, "mask": mask, "views": fused}

@@ -1,6 +1,6 @@
 """The slice of the reference's GaussianModel that the render / fusion path reads
 (model/gaussian_model.py:33-48 activations, :105-144 getters, :188-194 create_semantic).
-Training-state bookkeeping (densify / prune / optimiser / PLY IO) is out of scope."""
+Training-state bookkeeping (densify / prune / optimiser) is out of scope; PLY / npz IO lives in io_formats.py."""
 from __future__ import annotations
 
 import torch
@@ -102,3 +102,18 @@ class GaussianModel:
         P, dev = self._xyz.shape[0], self._xyz.device
         self._features_semantic = torch.zeros((P, dim), dtype=torch.float32, device=dev)
         self._times = torch.zeros((P, 1), dtype=torch.float32, device=dev)
+
+    # --- on-disk formats (model/gaussian_model.py:265-281, :288-344, :346-378) without plyfile
+    def save_ply(self, path):
+        from .io_formats import save_gaussian_ply
+        save_gaussian_ply(path, self)
+
+    def load_ply(self, path, device="cuda"):
+        from .io_formats import load_gaussian_ply
+        load_gaussian_ply(path, self, device=device)
+
+    def load_dynamic_npz(self, path, t, device="cuda"):
+        from .io_formats import load_dynamic_npz
+        if not hasattr(self, "_npz_cache"):
+            self._npz_cache = {}
+        load_dynamic_npz(path, t, self, device=device, cache=self._npz_cache)

@@ -88,3 +88,55 @@ def test_fusion_edge_cases():
     assert m0.shape == (0, 3)
     with pytest.raises(ValueError):
         mapper.compute_mapping(cam.world_view_transform, scene.xyz, np.zeros((10, 10), np.float32))
+
+
+def test_fuse_scene_rendered_depth_matches_host_round_trip():
+    """fuse_scene(depth="render") (depth stays on the device) == the reference sequence
+    render -> .cpu().numpy() -> compute_mapping (numpy oracle) -> gather/accumulate -> normalise, bit for bit."""
+    from semantic_gaussians_b200.fusion import fuse_scene
+    from semantic_gaussians_b200.gaussian_model import GaussianModel
+    from semantic_gaussians_b200.renderer import render
+    from semantic_gaussians_b200.scene_synth import make_scene, orbit_cameras
+    dev = torch.device("cuda:0")
+    P, C, w, h = 30000, 24, 160, 120
+    scene = make_scene(P, 5, sh=True)
+    pc = GaussianModel.from_activated(scene.xyz, scene.scales, scene.rotations, scene.opacity, shs=scene.shs, device=dev)
+    cams = orbit_cameras(6, 320, 240)            # native camera size differs from img_dim -> override_shape path
+    rng = np.random.default_rng(3)
+    fmaps = [torch.from_numpy(rng.standard_normal((C, h, w)).astype(np.float16)).to(dev) for _ in cams]
+
+    class Pipe:
+        convert_shs_python = False
+        compute_cov3d_python = False
+        debug = False
+
+    class View:
+        pass
+
+    views = []
+    for c in cams:
+        v = View()
+        v.image_width, v.image_height, v.FoVx, v.FoVy = c.image_width, c.image_height, c.FoVx, c.FoVy
+        v.world_view_transform = torch.as_tensor(c.world_view_transform, device=dev)
+        v.full_proj_transform = torch.as_tensor(c.full_proj_transform, device=dev)
+        v.camera_center = torch.as_tensor(c.camera_center, device=dev)
+        v.intrinsics = c.intrinsics()
+        views.append(v)
+    bg = torch.zeros(3, device=dev)
+    pc.create_semantic(C)
+    out = fuse_scene(pc, views, fmaps, Pipe, bg, [w, h], visibility_threshold=0.05, cut_boundary=4, depth="render", every=2)
+    assert out["views"] == 3
+
+    fs = np.zeros((P, C), np.float32)
+    cnt = np.zeros(P, np.float32)
+    for idx in range(0, 6, 2):
+        d = render(views[idx], pc, Pipe, bg, override_shape=[w, h])["depth"].cpu().numpy()[0]      # fusion.py:110-120
+        assert d.shape == (h, w) and d.dtype == np.float32
+        K = fo.rescale_intrinsics(views[idx].intrinsics, [w, h])
+        m = fo.compute_mapping(cams[idx].world_view_transform, scene.xyz, [w, h], K, 0.05, 4, d)
+        fo.accumulate(fmaps[idx].cpu().numpy(), m, fs, cnt)
+    seen = cnt > 0
+    fo.normalize(fs, cnt)
+    assert seen.sum() > 1000
+    assert np.array_equal(out["mask"].cpu().numpy(), seen)
+    assert np.array_equal(out["features"].cpu().numpy(), fs)
