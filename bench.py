@@ -182,6 +182,26 @@ def algorithmic_bytes(P, P_vis, R, C, W, H):
     return dict(alpha_pass=alpha, blend_fwd=fwd_blend, blend_bwd=chain, dfeature=dfeat, fwd=fwd_total, bwd=bwd_total)
 
 
+FMA_PEAK_TFLOPS = 70.5   # dependent-free FFMA loop on this pool's B200s (tools/microbench.cu)
+
+
+def fma_roofline(C, blended_pairs, per_stage):
+    """fp32 CUDA-core roof of the three C-wide contractions: achieved = algorithmic flops
+    (2*C per blended pair and contraction, zero-weight padding not counted) / stage time."""
+    out = {"peak_tflops": FMA_PEAK_TFLOPS, "peak_source": "measured FFMA micro-benchmark (tools/microbench.cu)",
+           "algorithmic_flops_per_contraction": 2 * C * blended_pairs, "kernels": {}}
+    for k in ("blend_fwd", "blend_bwd", "dfeature"):
+        ms = per_stage.get(k)
+        if ms:
+            tf = 2 * C * blended_pairs / (ms * 1e-3) * 1e-12
+            out["kernels"][k] = {"ms": ms, "achieved_tflops": tf, "frac": tf / FMA_PEAK_TFLOPS}
+    tot = sum(per_stage.get(k, 0.0) for k in ("blend_fwd", "blend_bwd", "dfeature", "alpha_pass"))
+    if tot:
+        out["achieved_tflops"] = 6 * C * blended_pairs / (tot * 1e-3) * 1e-12
+        out["frac"] = out["achieved_tflops"] / FMA_PEAK_TFLOPS
+    return out
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -324,6 +344,8 @@ def run_gpu(args, rank, world, local_rank):
         _lib.load().sgb_state_field(b"n_contrib", P_GAUSS, Rn, WIDTH, HEIGHT, None, None, img.data_ptr(),
                                     nc.data_ptr(), stream)
         ncontrib_mean = float(nc.float().mean())
+        blended_pairs = _lib.view_stat(ctx, 0)        # (pixel, Gaussian) pairs blended in this view
+        pool_chunks = _lib.view_stat(ctx, 1)
         del img, nc
     launches0 = _lib.launch_count(ctx)
     _lib.profile_enable(ctx, True)
@@ -373,13 +395,17 @@ def run_gpu(args, rank, world, local_rank):
                    "views_per_step": world, "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of per-Gaussian grads (feature grad overlapped with the chain backward)" if world > 1 else ""),
                    "l2": "inputs larger than L2 (1.0 GB feature table, 2.1 GB dL/dout, 2.1 GB output per step; 8 cycling views)",
                    "P_vis": P_vis, "R": int(Rn), "gaussians_per_tile_mean": Rn / (((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)),
-                   "n_contrib_mean": ncontrib_mean},
+                   "n_contrib_mean": ncontrib_mean, "n_blended_mean": blended_pairs / (WIDTH * HEIGHT),
+                   "tile_entries_mean": pool_chunks * 16 / (((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16))},
         "views_per_s": value * 1e6, "hbm_gbs_effective": eff_gbs, "hbm_frac_effective": eff_gbs / peak,
         "stage_ms": per_stage, "kernel_ms_per_step": kernel_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": ab[dom], "kernel_ms": dom_ms,
                      "peak_source": peak_src,
                      "note": "C=256 blend is fp32-FMA bound by design (no tensor cores, north_star); see DESIGN.md"},
+        # the C = 256 blend is three fp32 contractions on the CUDA cores (north_star rules out tensor cores):
+        # algorithmic flops = 2*C per blended (pixel, Gaussian) pair for each of forward, s-pass, dL/dfeature
+        "fma_roofline": fma_roofline(CHANNELS, blended_pairs, per_stage),
         "e2e": {"value": e2e_value, "unit": "Mviews/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 35 * 4 + HEIGHT * WIDTH * 4, "d2h_bytes_per_step": 4,
                 "api": "render_chn() + distillation loss + backward; camera + label map from pinned host memory"},

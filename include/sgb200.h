@@ -111,6 +111,10 @@ const char* sgb_profile_stage_name(int stage);
 /* Kernels of this library launched through ctx so far (library_calls = 0), or the number of
  * CUB device-wide calls (library_calls = 1; each is several kernels). */
 uint64_t sgb_ctx_launch_count(const sgb_ctx* ctx, int library_calls);
+/* Statistics of the most recent C > 4 view rendered through ctx (no synchronisation: the values were read
+ * back with the weight-pool header).  which = 0: blended (pixel, Gaussian) pairs, i.e. n-bar * W * H, the
+ * quantity the blend's algorithmic flops scale with; 1: 16-entry weight-row chunks in use.  -1 if unknown. */
+int64_t sgb_ctx_view_stat(const sgb_ctx* ctx, int which);
 /* Optional cudaEvent_t that sgb_backward records on its stream as soon as dL_dcolors (the (P, C)
  * feature gradient — the only large per-Gaussian gradient) is final, i.e. BEFORE the chain and
  * geometry gradient kernels.  A data-parallel caller lets its communication stream wait on this

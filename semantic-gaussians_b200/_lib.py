@@ -54,7 +54,7 @@ EXPORTS = (
     "sgb_forward_render", "sgb_backward", "sgb_mark_visible", "sgb_state_field", "sgb_fusion_map",
     "sgb_fusion_accumulate", "sgb_fusion_normalize", "sgb_profile_enable", "sgb_profile_read",
     "sgb_profile_num_stages", "sgb_profile_stage_name", "sgb_ctx_launch_count",
-    "sgb_ctx_set_feature_grad_event", "sgb_semantic_head", "sgb_feature_logits", "sgb_label_argmax",
+    "sgb_ctx_set_feature_grad_event", "sgb_semantic_head", "sgb_feature_logits", "sgb_label_argmax", "sgb_ctx_view_stat",
 )
 
 _lib = None
@@ -105,6 +105,8 @@ def load() -> C.CDLL:
         lib.sgb_ctx_launch_count.argtypes = [vp, C.c_int]
         lib.sgb_ctx_launch_count.restype = C.c_uint64
         lib.sgb_ctx_set_feature_grad_event.argtypes = [vp, vp]
+        lib.sgb_ctx_view_stat.argtypes = [vp, C.c_int]
+        lib.sgb_ctx_view_stat.restype = i64
         lib.sgb_semantic_head.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, vp, vp]
         lib.sgb_feature_logits.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
         lib.sgb_label_argmax.argtypes = [i32, i32, i64, vp, vp, vp]
@@ -150,6 +152,11 @@ def profile_read(ctx: int) -> dict:
 def set_feature_grad_event(ctx: int, cuda_event) -> None:
     """cuda_event: a cudaEvent_t handle (e.g. torch.cuda.Event.cuda_event after a first record) or None."""
     check(load().sgb_ctx_set_feature_grad_event(ctx, cuda_event), "sgb_ctx_set_feature_grad_event")
+
+
+def view_stat(ctx: int, which: int) -> int:
+    """0: blended (pixel, Gaussian) pairs of the last C > 4 view; 1: weight-row chunks in use."""
+    return int(load().sgb_ctx_view_stat(ctx, which))
 
 
 def launch_count(ctx: int) -> tuple:

@@ -243,6 +243,11 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, 
     return launch_geom_backward(*in, g, radii, cov3D, gr->dL_dcolors, *gr, s);
 }
 
+int64_t sgb_ctx_view_stat(const sgb_ctx* ctx, int which) {
+    if (!ctx) return -1;
+    return which == 0 ? ctx->stat_blended_pairs : which == 1 ? ctx->stat_pool_chunks : -1;
+}
+
 int sgb_ctx_set_feature_grad_event(sgb_ctx* ctx, void* cuda_event) {
     if (!ctx) { set_error("sgb_ctx_set_feature_grad_event: null ctx"); return SGB_E_INVALID; }
     ctx->feature_grad_event = (cudaEvent_t)cuda_event;

@@ -37,7 +37,7 @@ constexpr int kChunkEntries = 16;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 struct __align__(16) WChunk {
-    uint32_t next, prev, pad0, pad1;
+    uint32_t pad[4];
     uint2 meta[kChunkEntries];             // x: Gaussian id, y: bit w = strip (warp) w has a non-zero weight
     float w[kChunkEntries][SGB_TILE_PIX];  // alpha * T per pixel (tile-local index ty*16+tx)
 };
@@ -46,16 +46,26 @@ static_assert(sizeof(WChunk) % 16 == 0, "WChunk must keep 16-byte alignment in a
 struct PoolHdr {
     uint32_t counter;   // chunks handed out (keeps counting past capacity: the true demand)
     uint32_t overflow;  // set when counter ran past capacity (results invalid, caller retries)
+    unsigned long long blended;  // (pixel, Gaussian) pairs that were blended: n-bar * W * H (reported by bench.py)
 };
 
+// A tile's chunks are found through a DIRECTORY (no linked list, no pointer chasing): chunk k of tile t is
+// dir[dirbase[t] + k] with dirbase[t] = ranges[t].x / 16 + t.  The tile ranges are disjoint intervals of the
+// sorted instance list, a tile with `len` instances needs at most ceil(len / 16) chunks, and
+// floor(x/16) + ceil(len/16) <= floor((x+len)/16) + 1, so the regions cannot overlap and R/16 + tiles + 1
+// directory slots always suffice — no scan, no capacity guess.
 struct PoolView {
     PoolHdr* hdr;
-    uint32_t* head;   // [tiles] first chunk or kNone
-    uint32_t* tail;   // [tiles] last chunk or kNone
-    uint32_t* count;  // [tiles] entries
+    uint32_t* dirbase;  // [tiles] first directory slot of the tile
+    uint32_t* count;    // [tiles] entries
+    uint32_t* dir;      // [R/16 + tiles + 1] chunk indices
     WChunk* chunks;
     uint32_t capacity;
 };
+
+__device__ __forceinline__ uint32_t chunk_of(const PoolView& pool, uint32_t dbase, int k) {
+    return min(__ldg(pool.dir + dbase + k), pool.capacity - 1);
+}
 
 template <int N>
 __device__ __forceinline__ void xreduce_step(float (&v)[8], int lane, int step) {
@@ -103,12 +113,14 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     const int nbatches = (total + kAB - 1) / kAB;
+    const uint32_t dbase = range.x / kChunkEntries + (uint32_t)tile;
     if (tid == 0) { sm.cur_chunk = kNone; sm.s_last = 0; }
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
     float D = 15.0f;
     uint32_t n_tile = 0;  // entries appended so far (uniform)
+    uint32_t n_blend = 0; // Gaussians blended into this pixel
 
     for (int b = 0; b < nbatches; b++) {
         const int num_done = __syncthreads_count(done);  // forward.cu:310-312
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
                 }
             }
             sm.wbuf[j][tid] = w;
+            n_blend += (w != 0.f);
             if (__ballot_sync(0xffffffffu, w != 0.f)) my_mask |= 1u << j;
         }
         if (lane == 0) sm.wmask[warp] = my_mask;
@@ -169,10 +182,7 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
                             pool.hdr->overflow = 1;
                             nw = pool.capacity - 1;
                         }
-                        pool.chunks[nw].prev = cur;
-                        pool.chunks[nw].next = kNone;
-                        if (cur == kNone) pool.head[tile] = nw;
-                        else pool.chunks[cur].next = nw;
+                        pool.dir[dbase + e / kChunkEntries] = nw;
                         cur = nw;
                     }
                     sm.slot_chunk[k] = cur;
@@ -203,12 +213,13 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
         if (DEPTH) out_depth[pix_id] = D;
         atomicMax(&sm.s_last, last_contributor);
     }
+    n_blend = __reduce_add_sync(0xffffffffu, n_blend);
+    if (lane == 0 && n_blend) atomicAdd(&pool.hdr->blended, (unsigned long long)n_blend);
     __syncthreads();
     if (tid == 0) {
         tile_last[tile] = sm.s_last;
         pool.count[tile] = n_tile;
-        pool.tail[tile] = sm.cur_chunk;
-        if (n_tile == 0) pool.head[tile] = kNone;
+        pool.dirbase[tile] = dbase;
     }
 }
 
@@ -234,11 +245,11 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
         for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
 
     const uint32_t n = pool.count[tile];
-    uint32_t c = pool.head[tile];
+    const uint32_t dbase = pool.dirbase[tile];
     const int woff = warp * 32 + pg * 8;
     const int foff = ch0 + cg * MCH;
     for (uint32_t e = 0; e < n;) {
-        const WChunk* ck = pool.chunks + min(c, pool.capacity - 1);
+        const WChunk* ck = pool.chunks + chunk_of(pool, dbase, (int)(e / kChunkEntries));
         const int m = (int)min((uint32_t)kChunkEntries, n - e);
         for (int s = 0; s < m; s++) {
             const uint2 meta = ck->meta[s];
@@ -271,7 +282,6 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
             }
         }
         e += m;
-        c = ck->next;
     }
 
     // out = acc + T * bg (forward.cu:372-373)
@@ -327,34 +337,32 @@ constexpr int kSeg = 64;  // entries per backward segment (4 chunks); S[8 warps]
 //     dfeature  dF[G][64 ch]        = W[G][256 px]    . dL[256 px][64]   K = 256 px lane tile 4 entries x 8 ch
 // Register tiles make every product 64-128 FMAs per 4-6 shared-memory loads and need no cross-lane
 // reductions (an earlier shuffle-reduce formulation spent ~40 % of its issue slots on SHFL/FSEL/FADD).
-// chunk index holding the entry k places after the first entry of chunk c0: walks `next` pointers (k / 16 hops)
-__device__ __forceinline__ uint32_t chunk_at(const PoolView& pool, uint32_t c0, int k) {
-    uint32_t c = min(c0, pool.capacity - 1);
-    for (int h = k / kChunkEntries; h > 0; h--) c = min(pool.chunks[c].next, pool.capacity - 1);
-    return c;
-}
-
 // Forward GEMM with a TMA-fed ring.  With plain loads of the weight rows 67 % of the instructions were
 // packed FMAs but only 28 % of the issue slots were used — every warp waited an L2/DRAM round trip per
-// entry (ncu long_scoreboard 9.2 stalls per issue).  Here each staged Gaussian is two 1-D bulk
-// copies (cp.async.bulk: the 1 KB weight row and the 256 B feature slice) into a ring of NS stages
-// of ES entries guarded by full/empty mbarriers; warp 0 issues stage b+NS-1 after consuming stage b,
-// so up to (NS-1)*ES entries are in flight and no warp ever blocks on a global load.
-template <int CH, int ES, int NS>
+// entry (ncu long_scoreboard 9.2 stalls per issue).  Here one ring stage = one 16-entry chunk: per staged
+// Gaussian two 1-D bulk copies (cp.async.bulk: the 1 KB weight row and the 256 B feature slice), NS stages
+// guarded by full/empty mbarriers.  Warp 0 is producer AND consumer, so nothing it does for production may
+// block its math: the chunk indices come from the tile's directory (copied to shared memory up front, no
+// pointer chasing), the (id, mask) records of the NEXT batch are fetched into registers one whole batch of
+// math before they are needed, and the stage it refills is the one everybody left TWO batches ago, so the
+// empty-barrier wait is already satisfied (refilling the stage of the previous batch coupled warp 0 to
+// the slowest warp on every batch: ncu showed the FMA pipe 50 % idle with long-scoreboard stalls on top).
+template <int CH, int NS>
 __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
     int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
     const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
     constexpr int MCH = CH / 8;
-    static_assert(ES <= 16, "one lane of warp 0 per staged entry; mask array padded to 16");
+    constexpr int ES = kChunkEntries;  // entries per stage
+    constexpr int LA = NS - 2;         // batches in flight ahead of the one being consumed
+    constexpr int kDirCap = 192;       // directory entries cached in shared memory (3072 active Gaussians / tile)
     struct Stage {
         float w[ES][SGB_TILE_PIX];
         float f[ES][CH];
-        uint32_t strips[ES];  // bit w: strip (warp) w has a non-zero weight for this entry
-        uint32_t pad[16 - ES];  // keeps sizeof(Stage) a multiple of 16 bytes (ES <= 16)
     };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage* stg = reinterpret_cast<Stage*>(smem_raw);
     __shared__ uint64_t full_bar[NS], empty_bar[NS];
+    __shared__ uint32_t Cdir[kDirCap];
 
     const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
     const int nchunksC = (C + CH - 1) / CH;
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
 
     const uint32_t n = pool.count[tile];
     const int nb = (int)((n + ES - 1) / ES);
+    const uint32_t dbase = pool.dirbase[tile];
     if (tid == 0) {
         for (int i = 0; i < NS; i++) {
             mbar_init(&full_bar[i], 1);
@@ -374,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         }
         mbar_fence_init();
     }
+    for (int k = tid; k < min(nb, kDirCap); k += kThreads) Cdir[k] = chunk_of(pool, dbase, k);
     if (nch < CH)  // zero the never-written tail of every feature row once
         for (int e = tid; e < NS * ES * CH; e += kThreads) {
             const int k = e % CH;
@@ -381,34 +391,39 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         }
     __syncthreads();
 
-    // producer state (warp 0): chunk holding the first entry of the next batch to issue
-    uint32_t pc = pool.head[tile];
-    int pb = 0;  // next batch to issue
-    auto produce = [&]() {  // warp 0, converged
-        const int st = pb % NS;
-        const int base = pb * ES;
-        const int cnt = min(ES, (int)n - base);
-        if (pb >= NS) mbar_wait(&empty_bar[st], (uint32_t)(((pb / NS) - 1) & 1));  // all 8 warps released it
+    // ---- producer (warp 0, lanes 0..15 = entry slots of a chunk)
+    auto chunk_ptr = [&](int bi) {
+        return pool.chunks + (bi < kDirCap ? Cdir[bi] : chunk_of(pool, dbase, bi));
+    };
+    auto load_meta = [&](int bi) {  // (Gaussian id, strip mask) of this lane's entry of batch bi
+        uint2 m = make_uint2(0u, 0u);
+        if (bi < nb && lane < min(ES, (int)n - bi * ES)) m = __ldg(&chunk_ptr(bi)->meta[lane]);
+        return m;
+    };
+    auto issue = [&](int bi, uint2 meta) {  // warp 0, converged; bi < nb
+        const int st = bi % NS;
+        const int cnt = min(ES, (int)n - bi * ES);
+        if (bi >= NS) mbar_wait(&empty_bar[st], (uint32_t)(((bi / NS) - 1) & 1));  // batch bi-NS released by all warps
         if (lane < cnt) {
-            const uint32_t c = chunk_at(pool, pc, lane);
-            const WChunk* ck = pool.chunks + c;
-            const int s = (base + lane) & (kChunkEntries - 1);
-            const uint2 meta = ck->meta[s];
-            stg[st].strips[lane] = meta.y;
-            bulk_g2s(&stg[st].w[lane][0], &ck->w[s][0], SGB_TILE_PIX * 4u, &full_bar[st]);
+            const WChunk* ck = chunk_ptr(bi);
+            bulk_g2s(&stg[st].w[lane][0], &ck->w[lane][0], SGB_TILE_PIX * 4u, &full_bar[st]);
             bulk_g2s(&stg[st].f[lane][0], features + (size_t)meta.x * C + ch0, (uint32_t)nch * 4u, &full_bar[st]);
         }
-        __syncwarp();  // the strip masks of all lanes precede lane 0's (releasing) arrive
+        __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], (uint32_t)cnt * (SGB_TILE_PIX * 4u + (uint32_t)nch * 4u));
-        // advance to the chunk holding entry base + ES
-        const int hops = ((base & (kChunkEntries - 1)) + ES) / kChunkEntries;
-        uint32_t c = min(pc, pool.capacity - 1);
-        for (int h = 0; h < hops; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
-        pc = c;
-        pb++;
     };
-    if (warp == 0)
-        for (int i = 0; i < NS - 1 && pb < nb; i++) produce();
+    uint2 meta_next = make_uint2(0u, 0u);  // record of batch `pb`, the next one to issue
+    int pb = 0;
+    if (warp == 0) {
+        uint2 m[LA];
+#pragma unroll
+        for (int i = 0; i < LA; i++) m[i] = load_meta(i);  // independent loads, one round trip
+#pragma unroll
+        for (int i = 0; i < LA; i++)
+            if (i < nb) issue(i, m[i]);
+        pb = min(LA, nb);
+        meta_next = load_meta(pb);
+    }
 
     float2 acc[8][MCH / 2];
 #pragma unroll
@@ -417,31 +432,40 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
 
     const int woff = warp * 32 + pg * 8;
+    auto entry = [&](const Stage& sg, int e) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sg.w[e][woff]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sg.w[e][woff + 4]);
+        float2 f[MCH / 2];
+#pragma unroll
+        for (int q = 0; q < MCH / 4; q++) {
+            const float4 t = *reinterpret_cast<const float4*>(&sg.f[e][cg * MCH + 4 * q]);
+            f[2 * q] = make_float2(t.x, t.y);
+            f[2 * q + 1] = make_float2(t.z, t.w);
+        }
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float2 w2 = make_float2(wv[i], wv[i]);
+#pragma unroll
+            for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
+        }
+    };
     for (int b = 0; b < nb; b++) {
         const int st = b % NS;
         const int cnt = min(ES, (int)n - b * ES);
-        if (warp == 0 && pb < nb) produce();  // refill the stage everybody left one batch ago
+        if (warp == 0 && pb < nb) {  // refill the stage of batch b-2 with batch b+LA
+            issue(pb, meta_next);
+            pb++;
+            meta_next = load_meta(pb);  // lands while this batch is being consumed
+        }
         mbar_wait(&full_bar[st], (uint32_t)((b / NS) & 1));
-#pragma unroll 4
-        for (int e = 0; e < cnt; e++) {
-            // dense on purpose: skipping strips whose 32 weights are all zero (about 15 % of the entries)
-            // breaks the unrolled load/FMA software pipeline and measured 10 % slower on K3
-            const float4 w0 = *reinterpret_cast<const float4*>(&stg[st].w[e][woff]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&stg[st].w[e][woff + 4]);
-            float2 f[MCH / 2];
+        // dense on purpose: skipping strips whose 32 weights are all zero (about 15 % of the entries)
+        // breaks the unrolled load/FMA software pipeline and measured 10 % slower on K3
+        if (cnt == ES) {
 #pragma unroll
-            for (int q = 0; q < MCH / 4; q++) {
-                const float4 t = *reinterpret_cast<const float4*>(&stg[st].f[e][cg * MCH + 4 * q]);
-                f[2 * q] = make_float2(t.x, t.y);
-                f[2 * q + 1] = make_float2(t.z, t.w);
-            }
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float2 w2 = make_float2(wv[i], wv[i]);
-#pragma unroll
-                for (int k = 0; k < MCH / 2; k++) acc[i][k] = ffma2(f[k], w2, acc[i][k]);
-            }
+            for (int e = 0; e < ES; e++) entry(stg[st], e);
+        } else {
+            for (int e = 0; e < cnt; e++) entry(stg[st], e);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[st]);
@@ -526,13 +550,12 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     cp_async_commit();
 
     const int eg = lane >> 3, cg = lane & 7;
-    uint32_t c0 = pool.head[tile];
+    const uint32_t dbase = pool.dirbase[tile];
     for (uint32_t base = 0; base < n; base += 128) {
         const int cnt = (int)min(128u, n - base);
         __syncthreads();  // previous pass done with Wrow / Gid
         if (tid < cnt) {
-            const uint32_t c = chunk_at(pool, c0, tid);
-            const WChunk* ck = pool.chunks + c;
+            const WChunk* ck = pool.chunks + chunk_of(pool, dbase, (int)((base + tid) / kChunkEntries));
             const int s = (base + tid) & (kChunkEntries - 1);
             Wrow[tid] = &ck->w[s][0];
             Gid[tid] = ck->meta[s].x;
@@ -561,20 +584,42 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                 if (sl + 1 < SGB_TILE_PIX / 32) { issue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
                 else cp_async_wait<0>();
                 __syncwarp();
-#pragma unroll 2
-                for (int p4 = 0; p4 < 8; p4++) {
-                    float4 wq[4];
+                // Fully unrolled and software-pipelined by hand: ptxas otherwise issues every LDS right in
+                // front of its first consumer (ncu: half of all stall samples were short-scoreboard waits on
+                // those FFMA2s).  dL rows are fetched two K-steps ahead, the next pixel quad's weights while
+                // the current quad is being consumed.
+                const float* dbase = &dLs[cg][sl * 32];
+                const float* wbase = &wsl[buf][eg][0];
+                auto ld_d = [&](int step) {  // step = p4 * 8 + k
+                    return *reinterpret_cast<const float4*>(dbase + (step & 7) * 8 * DP + (step >> 3) * 4);
+                };
+                float4 wq[4], wn[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) wq[j] = *reinterpret_cast<const float4*>(&wsl[buf][eg + 4 * j][p4 * 4]);
-                    const int px = sl * 32 + p4 * 4;
+                for (int j = 0; j < 4; j++) wq[j] = *reinterpret_cast<const float4*>(wbase + 4 * j * WP);
+                float4 d0 = ld_d(0), d1 = ld_d(1);
+#pragma unroll
+                for (int p4 = 0; p4 < 8; p4++) {
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
-                        const float4 d = *reinterpret_cast<const float4*>(&dLs[cg + 8 * k][px]);
+                        const int step = p4 * 8 + k;
+                        float4 d2 = d1;
+                        if (step + 2 < 64) d2 = ld_d(step + 2);
+                        if (k == 2 && p4 + 1 < 8) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                wn[j] = *reinterpret_cast<const float4*>(wbase + 4 * j * WP + (p4 + 1) * 4);
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            acc[j][k] = ffma2(make_float2(wq[j].x, wq[j].y), make_float2(d.x, d.y), acc[j][k]);
-                            acc[j][k] = ffma2(make_float2(wq[j].z, wq[j].w), make_float2(d.z, d.w), acc[j][k]);
+                            acc[j][k] = ffma2(make_float2(wq[j].x, wq[j].y), make_float2(d0.x, d0.y), acc[j][k]);
+                            acc[j][k] = ffma2(make_float2(wq[j].z, wq[j].w), make_float2(d0.z, d0.w), acc[j][k]);
                         }
+                        d0 = d1;
+                        d1 = d2;
+                    }
+                    if (p4 + 1 < 8) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) wq[j] = wn[j];
                     }
                 }
                 __syncwarp();  // slab `buf` may be refilled by the next issue
@@ -590,10 +635,6 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                 }
             }
         }
-        // first chunk of the next pass: 128 / 16 hops
-        uint32_t c = min(c0, pool.capacity - 1);
-        for (int h = 0; h < 128 / kChunkEntries && base + 128 < n; h++) c = min(pool.chunks[c].next, pool.capacity - 1);
-        c0 = c;
     }
 }
 
@@ -629,6 +670,7 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
     const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
     const uint32_t n = pool.count[tile];
     if (n == 0) return;
+    const uint32_t dbase = pool.dirbase[tile];
 
     const size_t plane = (size_t)H * W;
     const bool rows16 = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0);
@@ -653,9 +695,7 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
         __syncthreads();  // previous segment done with S / Wrow / Meta / FT
         if (tid < kSeg) {
             if (tid < cnt) {
-                uint32_t c = min(pool.head[tile], pool.capacity - 1);
-                for (int h = (base + tid) / kChunkEntries; h > 0; h--) c = min(pool.chunks[c].next, pool.capacity - 1);
-                const WChunk* ck = pool.chunks + c;
+                const WChunk* ck = pool.chunks + chunk_of(pool, dbase, (base + tid) / kChunkEntries);
                 const int s = (base + tid) & (kChunkEntries - 1);
                 Wrow[tid] = &ck->w[s][0];
                 const uint2 mt = ck->meta[s];
@@ -821,17 +861,17 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
 }
 
 // ------------------------------------------------------------------------------------ host side
-size_t pool_bytes(int tiles, uint32_t chunks, PoolView* v, void* base) {
+size_t pool_bytes(int tiles, uint32_t chunks, int64_t R, PoolView* v, void* base) {
     size_t off = 0;
     char* p = (char*)base;
     auto take = [&](size_t n) { size_t o = off; off += align_up(n); return p ? p + o : nullptr; };
     void* hdr = take(sizeof(PoolHdr));
-    void* head = take(4 * (size_t)tiles);
-    void* tail = take(4 * (size_t)tiles);
+    void* dbase = take(4 * (size_t)tiles);
     void* cnt = take(4 * (size_t)tiles);
+    void* dir = take(4 * ((size_t)(R / kChunkEntries) + (size_t)tiles + 1));
     void* ch = take(sizeof(WChunk) * (size_t)chunks);
     if (v) {
-        v->hdr = (PoolHdr*)hdr; v->head = (uint32_t*)head; v->tail = (uint32_t*)tail; v->count = (uint32_t*)cnt;
+        v->hdr = (PoolHdr*)hdr; v->dirbase = (uint32_t*)dbase; v->count = (uint32_t*)cnt; v->dir = (uint32_t*)dir;
         v->chunks = (WChunk*)ch; v->capacity = chunks;
     }
     return off;
@@ -848,7 +888,7 @@ static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Ge
     // the same ctx (the usual training step): same binning state, same sizes, nothing ran in between.
     if (ctx->pool_valid && ctx->pool_key_bin == (const void*)b.point_list && ctx->pool_key_R == R &&
         ctx->pool_key_W == in.W && ctx->pool_key_H == in.H && ctx->pool_key_P == in.P && !out_depth) {
-        pool_bytes(tiles, ctx->pool_key_chunks, pv, ctx->pool.p);
+        pool_bytes(tiles, ctx->pool_key_chunks, R, pv, ctx->pool.p);
         return SGB_OK;
     }
     ctx->pool_valid = false;
@@ -867,9 +907,9 @@ static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Ge
     }
     for (int attempt = 0; attempt < 4; attempt++) {
         const uint32_t chunks = (uint32_t)guess;
-        int rc = ctx->pool.ensure(pool_bytes(tiles, chunks, nullptr, nullptr));
+        int rc = ctx->pool.ensure(pool_bytes(tiles, chunks, R, nullptr, nullptr));
         if (rc) return rc;
-        pool_bytes(tiles, chunks, pv, ctx->pool.p);
+        pool_bytes(tiles, chunks, R, pv, ctx->pool.p);
         SGB_CUDA(cudaMemsetAsync(pv->hdr, 0, sizeof(PoolHdr), s));
         {
             StageTimer t(ctx, ST_ALPHA, s);
@@ -887,6 +927,8 @@ static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Ge
         SGB_CUDA(cudaStreamSynchronize(s));
         const uint32_t used = h[0], overflow = h[1];
         if (!overflow) {
+            ctx->stat_blended_pairs = (int64_t)(*reinterpret_cast<const unsigned long long*>(h + 2));
+            ctx->stat_pool_chunks = used;
             if (used > ctx->pool_chunks_hint) ctx->pool_chunks_hint = used + used / 16 + 16;
             ctx->pool_valid = true;
             ctx->pool_key_bin = (const void*)b.point_list;
@@ -914,17 +956,16 @@ int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVie
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
     if (vec) {
-        constexpr int ES = 8, NS = 8;
-        const size_t smem_f = (size_t)NS * (ES * (SGB_TILE_PIX + 64) + 16) * sizeof(float);
+        constexpr int NS = 5;
+        const size_t smem_f = (size_t)NS * kChunkEntries * (SGB_TILE_PIX + 64) * sizeof(float);
         static bool fattr = false;
         if (!fattr) {
-            SGB_CUDA(cudaFuncSetAttribute(blend_forward_tma_kernel<64, ES, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            SGB_CUDA(cudaFuncSetAttribute(blend_forward_tma_kernel<64, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_f));
             fattr = true;
         }
-        blend_forward_tma_kernel<64, ES, NS><<<tiles * chunks, kThreads, smem_f, s>>>(in.W, in.H, in.C, colors,
-                                                                                      in.background, im.final_T, pv,
-                                                                                      out_color);
+        blend_forward_tma_kernel<64, NS><<<tiles * chunks, kThreads, smem_f, s>>>(in.W, in.H, in.C, colors, in.background,
+                                                                                  im.final_T, pv, out_color);
     } else {
         // feature rows that are not 16-byte aligned slices (C % 4 != 0) cannot be bulk-copied: plain loads
         blend_forward_v3_kernel<64, false><<<tiles * chunks, kThreads, 0, s>>>(in.W, in.H, in.C, colors, in.background,

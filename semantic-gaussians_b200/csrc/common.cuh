@@ -135,6 +135,8 @@ struct sgb_ctx {
     int pool_key_W = 0, pool_key_H = 0, pool_key_P = 0;
     uint32_t pool_key_chunks = 0;
     int64_t* pinned = nullptr;  // host-pinned readback slot(s)
+    int64_t stat_blended_pairs = 0;  // last alpha pass: blended (pixel, Gaussian) pairs
+    int64_t stat_pool_chunks = 0;    // last alpha pass: 16-entry weight-row chunks in use
     cudaEvent_t feature_grad_event = nullptr;  // caller-owned; recorded when dL_dcolors is final (sgb200.h)
     // cached layout of the last sgb_forward_geometry call (consumed by sgb_forward_render)
     int64_t last_P = 0;
