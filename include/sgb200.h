@@ -222,6 +222,13 @@ int sgb_feature_logits(int32_t P, int32_t C, int32_t K, int32_t Kpad, const floa
                        float* out, void* stream);
 int sgb_label_argmax(int32_t K, int32_t first_class, int64_t N, const float* planes, int64_t* label, void* stream);
 
+/* ---- 3-nearest-neighbour mean squared distance: `distCUDA2` of the reference's
+ * simple-knn extension (submodules/simple-knn/simple_knn.cu:185-220, spatial.cu), used by
+ * GaussianModel.create_from_pcd (model/gaussian_model.py:150-186).  points (P,3) fp32 device, mean_dist2 (P) fp32
+ * device: (d1+d2+d3)/3 of the three smallest squared distances to OTHER points (exact, bit-identical to the
+ * reference).  Fewer than 4 points leave FLT_MAX terms, as in the reference. */
+int sgb_knn_mean_dist2(sgb_ctx* ctx, int32_t P, const float* points, float* mean_dist2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

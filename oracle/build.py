@@ -118,6 +118,26 @@ def build_ref(verbose: bool = False):
     return built
 
 
+def build_ref_knn(verbose: bool = False):
+    """oracle/_ref/libref_knn.so: the unmodified reference simple_knn.cu + oracle/knn_shim.cu."""
+    os.makedirs(REF_OUT, exist_ok=True)
+    out = os.path.join(REF_OUT, "libref_knn.so")
+    srcdir = os.path.join(REF_ROOT, "simple-knn")
+    if not os.path.isdir(srcdir):
+        return out if os.path.exists(out) else None
+    src = os.path.join(srcdir, "simple_knn.cu")
+    shim = os.path.join(HERE, "knn_shim.cu")
+    if _newer(out, [src, shim, os.path.abspath(__file__)]):
+        return out
+    # -include cfloat: simple_knn.cu uses FLT_MAX without the header (same class of omission as cstdint above)
+    _run(["nvcc", *ARCH, "-O3", "-std=c++17", "-w", "-include", "cfloat", "-Xcompiler", "-fPIC", "-shared",
+          f"-I{srcdir}", "-o", out, shim, src])
+    if verbose:
+        print("built", out)
+    return out
+
+
 if __name__ == "__main__":
     build_oracle(verbose=True)
     print("\n".join(build_ref(verbose=True)))
+    print(build_ref_knn(verbose=True))

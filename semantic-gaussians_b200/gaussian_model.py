@@ -97,6 +97,31 @@ class GaussianModel:
         L = build_scaling_rotation(scaling_modifier * self.get_scaling, self._rotation)
         return strip_symmetric(world_rotate.transpose(0, 1) @ L @ L.transpose(1, 2) @ world_rotate)
 
+    def create_from_pcd(self, points, colors, spatial_lr_scale: float = 1.0, device="cuda"):
+        """model/gaussian_model.py:150-186: initialise from a point cloud — SH dc from the colours, isotropic
+        log-scales from the mean squared distance to the 3 nearest neighbours (distCUDA2, clamped at 1e-7),
+        identity rotations, opacity 0.1.  ``points`` (P,3), ``colors`` (P,3) in [0,1] (numpy or torch)."""
+        from .simple_knn._C import distCUDA2
+        self.spatial_lr_scale = spatial_lr_scale
+        t = lambda a: torch.as_tensor(a).float().to(device)
+        xyz = t(points).contiguous()
+        fused_color = (t(colors) - 0.5) / 0.28209479177387814                     # RGB2SH, utils/sh_utils.py:118
+        n = xyz.shape[0]
+        features = torch.zeros((n, 3, (self.max_sh_degree + 1) ** 2), dtype=torch.float32, device=device)
+        features[:, :3, 0] = fused_color
+        dist2 = torch.clamp_min(distCUDA2(xyz), 0.0000001)
+        self._xyz = xyz
+        self._features_dc = features[:, :, 0:1].transpose(1, 2).contiguous()
+        self._features_rest = features[:, :, 1:].transpose(1, 2).contiguous()
+        self._scaling = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+        rots = torch.zeros((n, 4), device=device)
+        rots[:, 0] = 1
+        self._rotation = rots
+        op = 0.1 * torch.ones((n, 1), dtype=torch.float32, device=device)
+        self._opacity = torch.log(op / (1 - op))                                   # inverse_sigmoid
+        self.max_radii2D = torch.zeros((n,), device=device)
+        return self
+
     def create_semantic(self, dim: int):
         """model/gaussian_model.py:188-194: zero per-Gaussian feature sums and view counts."""
         P, dev = self._xyz.shape[0], self._xyz.device
