@@ -122,19 +122,40 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
     uint32_t n_tile = 0;  // entries appended so far (uniform)
     uint32_t n_blend = 0; // Gaussians blended into this pixel
 
+    // Staging of the (id, splat record) batches is software-pipelined in warp 0's registers: the ids run two
+    // batches ahead, the records (a dependent gather through the id) one batch ahead, so neither round trip
+    // sits between two batches of the chain (it used to: two dependent L2/DRAM latencies per 32 entries).
+    auto load_id = [&](int bb) -> uint32_t {
+        const int i = bb * kAB + tid;
+        return (tid < kAB && bb < nbatches && i < total) ? __ldg(point_list + range.x + i) : 0u;
+    };
+    uint32_t id_cur = load_id(0), id_nxt = load_id(1);
+    float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA;
+    if (tid < kAB && tid < total) {
+        const float4* rp = reinterpret_cast<const float4*>(rec + id_cur);
+        rA = __ldg(rp);
+        rB = __ldg(rp + 1);
+    }
     for (int b = 0; b < nbatches; b++) {
         const int num_done = __syncthreads_count(done);  // forward.cu:310-312
         if (num_done == kThreads) break;
         const int base = b * kAB;
         const int cnt = min(kAB, total - base);
         if (tid < cnt) {
-            const uint32_t id = point_list[range.x + base + tid];
-            sm.ids[tid] = id;
-            const float4* rp = reinterpret_cast<const float4*>(rec + id);
-            sm.recA[tid] = __ldg(rp);
-            sm.recB[tid] = __ldg(rp + 1);
+            sm.ids[tid] = id_cur;
+            sm.recA[tid] = rA;
+            sm.recB[tid] = rB;
         }
         __syncthreads();
+        if (tid < kAB) {  // records of batch b+1 (its ids are already here), ids of batch b+2
+            id_cur = id_nxt;
+            if (base + kAB + tid < total) {
+                const float4* rp = reinterpret_cast<const float4*>(rec + id_cur);
+                rA = __ldg(rp);
+                rB = __ldg(rp + 1);
+            }
+            id_nxt = load_id(b + 2);
+        }
         uint32_t my_mask = 0;
         for (int j = 0; j < cnt; j++) {
             float w = 0.f;
@@ -363,6 +384,8 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
     Stage* stg = reinterpret_cast<Stage*>(smem_raw);
     __shared__ uint64_t full_bar[NS], empty_bar[NS];
     __shared__ uint32_t Cdir[kDirCap];
+    __shared__ __align__(16) float Tsm[SGB_TILE_PIX];  // final_T of the tile (the epilogue used to stall on these loads)
+    __shared__ float bgS[CH];
 
     const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
     const int nchunksC = (C + CH - 1) / CH;
@@ -384,6 +407,11 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         mbar_fence_init();
     }
     for (int k = tid; k < min(nb, kDirCap); k += kThreads) Cdir[k] = chunk_of(pool, dbase, k);
+    {
+        const uint32_t x = pix_min.x + (tid & (SGB_TILE - 1)), y = pix_min.y + (tid >> 4);
+        Tsm[tid] = (x < (uint32_t)W && y < (uint32_t)H) ? final_T[(size_t)W * y + x] : 0.f;
+        if (tid < nch) bgS[tid] = bg_color[ch0 + tid];
+    }
     if (nch < CH)  // zero the never-written tail of every feature row once
         for (int e = tid; e < NS * ES * CH; e += kThreads) {
             const int k = e % CH;
@@ -476,14 +504,14 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
     if (row < (uint32_t)H) {
         const size_t plane = (size_t)H * W;
         const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
-        float Tv[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) Tv[i] = (col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+        const float4 t0 = *reinterpret_cast<const float4*>(&Tsm[(2 * warp + (pg >> 1)) * SGB_TILE + (pg & 1) * 8]);
+        const float4 t1 = *reinterpret_cast<const float4*>(&Tsm[(2 * warp + (pg >> 1)) * SGB_TILE + (pg & 1) * 8 + 4]);
+        const float Tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
         for (int k = 0; k < MCH; k++) {
             const int chl = cg * MCH + k;
             if (chl >= nch) continue;
-            const float bgc = bg_color[ch0 + chl];
+            const float bgc = bgS[chl];
             float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
             float o[8];
 #pragma unroll
@@ -528,7 +556,8 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     const int nch = min(CH, C - ch0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = pool.count[tile];
-    if (n == 0) return;
+    if (n == 0) return;  // (empty tiles are common: returning before the 64 KB dL copy matters)
+    const uint32_t dbase = __ldg(pool.dirbase + tile);
     const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
     const size_t plane = (size_t)H * W;
     const bool rows16 = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0;
@@ -550,7 +579,6 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     cp_async_commit();
 
     const int eg = lane >> 3, cg = lane & 7;
-    const uint32_t dbase = pool.dirbase[tile];
     for (uint32_t base = 0; base < n; base += 128) {
         const int cnt = (int)min(128u, n - base);
         __syncthreads();  // previous pass done with Wrow / Gid
