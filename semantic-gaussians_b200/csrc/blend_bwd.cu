@@ -256,10 +256,9 @@ int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, con
     const int chunks = (in.C + CH - 1) / CH;
     const size_t smem = sizeof(BwdSmem<CH>);
     auto kern = blend_backward_kernel<CH, BULK>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     kern<<<dim3(tiles, chunks), kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, in.C, in.background, g.rec,
                                                     colors, im.final_T, im.n_contrib, im.tile_last, dL_dpix,

@@ -182,10 +182,9 @@ int launch_one(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, con
     const int chunks = (in.C + CH - 1) / CH;
     const size_t smem = 2 * sizeof(FwdStage<CH>);
     auto kern = blend_forward_kernel<CH, BULK, EXACT, DEPTH>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     kern<<<dim3(tiles, chunks), kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, in.C, g.rec, colors,
                                                     in.background, im.final_T, im.n_contrib, im.tile_last,

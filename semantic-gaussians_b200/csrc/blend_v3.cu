@@ -927,11 +927,10 @@ static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Ge
     if (guess < ctx->pool_chunks_hint) guess = ctx->pool_chunks_hint;
     if (guess < 16) guess = 16;
     const size_t smem = sizeof(AlphaSmem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     for (int attempt = 0; attempt < 4; attempt++) {
         const uint32_t chunks = (uint32_t)guess;
@@ -986,11 +985,10 @@ int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVie
     if (vec) {
         constexpr int NS = 5;
         const size_t smem_f = (size_t)NS * kChunkEntries * (SGB_TILE_PIX + 64) * sizeof(float);
-        static bool fattr = false;
-        if (!fattr) {
+        static DeviceOnce fattr;
+        if (fattr.first_use_on_device()) {
             SGB_CUDA(cudaFuncSetAttribute(blend_forward_tma_kernel<64, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_f));
-            fattr = true;
         }
         blend_forward_tma_kernel<64, NS><<<tiles * chunks, kThreads, smem_f, s>>>(in.W, in.H, in.C, colors, in.background,
                                                                                   im.final_T, pv, out_color);
@@ -1015,12 +1013,11 @@ int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVi
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     const size_t smem_g = sizeof(float) * (8 * kSeg * 32 + 2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
     const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-        attr_set = true;
     }
     // dL/dfeature first: it needs only the weight rows and dL/dout, and it is the one large
     // gradient, so a data-parallel caller can start reducing it while the chain runs (sgb200.h)

@@ -159,6 +159,21 @@ struct StageTimer {  // RAII event pair around one stage
     }
 };
 
+// cudaFuncSetAttribute is per device: a process-wide "done" flag would leave the second device of a
+// single-process multi-GPU caller without its opt-in shared-memory size.  Returns true the first time it is
+// called with this flag array on the current device.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first_use_on_device() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------ stage launchers
 int launch_preprocess(const sgb_view_inputs& in, GeomView g, int32_t* radii, uint32_t* depth_keys,
                       cudaStream_t s);

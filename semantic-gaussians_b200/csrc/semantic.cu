@@ -329,10 +329,9 @@ void launch_head_t(int C, int K, long long N, const float* render, const float* 
     const unsigned blocks = (unsigned)((N + kHeadBlockPix - 1) / kHeadBlockPix);  // 1024 pixels per CTA either way
     const size_t smem_tma = kHeadRingBytes + sizeof(float) * (size_t)C * NK4 * 4;
     if (vec && smem_tma <= 224 * 1024 && (!label || (reinterpret_cast<uintptr_t>(label) & 15) == 0)) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first_use_on_device()) {
             cudaFuncSetAttribute(semantic_head_tma_kernel<NK4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-            attr_set = true;
         }
         semantic_head_tma_kernel<NK4><<<blocks, kTmaThreads, smem_tma, s>>>(C, K, N, render, text, first_class, sim,
                                                                             label, best_val, k0, multi);
@@ -386,10 +385,9 @@ static int launch_logits_t(int P, int C, int K, int Kpad, int k0, const float* f
         set_error("sgb_feature_logits: C = %d too large (class embeddings must fit shared memory)", C);
         return SGB_E_INVALID;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(feature_logits_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     const int blocks = min((P + 7) / 8, 148 * 4);
     feature_logits_kernel<KC><<<blocks, 256, smem, s>>>(P, C, K, Kpad, k0, features, text, out);
