@@ -1,6 +1,6 @@
 """The slice of the reference's GaussianModel that the render / fusion path reads
 (model/gaussian_model.py:33-48 activations, :105-144 getters, :188-194 create_semantic).
-Training-state bookkeeping (densify / prune / optimiser) is out of scope; PLY / npz IO lives in io_formats.py."""
+Density control / optimiser bookkeeping lives in densify.py (mixin), PLY / npz IO in io_formats.py."""
 from __future__ import annotations
 
 import torch
@@ -36,7 +36,10 @@ def strip_symmetric(sym: torch.Tensor) -> torch.Tensor:
     return torch.stack([sym[:, 0, 0], sym[:, 0, 1], sym[:, 0, 2], sym[:, 1, 1], sym[:, 1, 2], sym[:, 2, 2]], dim=1)
 
 
-class GaussianModel:
+from .densify import DensifyMixin  # noqa: E402
+
+
+class GaussianModel(DensifyMixin):
     """Parameter container with the reference's raw-parameter conventions: log scales, logit
     opacities, unnormalised quaternions, SH as (P,1,3) dc + (P,15,3) rest."""
 
