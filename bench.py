@@ -210,6 +210,7 @@ def run_gpu(args, rank, world, local_rank):
     from semantic_gaussians_b200.gaussian_model import GaussianModel
     from semantic_gaussians_b200.renderer import render_chn
     from semantic_gaussians_b200.scene_synth import make_scene, orbit_cameras
+    from semantic_gaussians_b200.semantic import distill_loss_and_grad
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
@@ -291,7 +292,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # the loss is read back the way training loops do it: an asynchronous 4-byte copy into pinned memory each
     # step, consumed one step later (and the last one inside the timed region), so the host keeps launching
-    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
     e2e_losses = []
 
@@ -303,10 +304,9 @@ def run_gpu(args, rank, world, local_rank):
         cam_dev.full_proj_transform = cam_buf[16:32].view(4, 4)
         cam_dev.camera_center = cam_buf[32:35]
         out = render_chn(cam_dev, pc, Pipe, bg, num_channels=CHANNELS, override_color=feats)
-        # open-vocabulary distillation loss  L = -mean_p <render[:, p], E[label(p)]>  and its gradient
-        dL = class_emb_t.index_select(1, label_buf.view(-1).long()).view(CHANNELS, HEIGHT, WIDTH)
-        loss = torch.dot(out["render"].detach().reshape(-1), dL.reshape(-1))
-        loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H 4 B
+        # open-vocabulary distillation loss  L = -mean <render[:, p], E[label(p)]>  and its gradient, one fused pass
+        loss, dL = distill_loss_and_grad(out["render"], class_emb, label_buf)
+        loss_host[i % 2].copy_(loss.reshape(1), non_blocking=True)            # D2H 8 B (float64 scalar)
         loss_ev[i % 2].record()
         out["render"].backward(dL)
         allreduce_grads()
@@ -424,8 +424,8 @@ def run_gpu(args, rank, world, local_rank):
         # algorithmic flops = 2*C per blended (pixel, Gaussian) pair for each of forward, s-pass, dL/dfeature
         "fma_roofline": fma_roofline(CHANNELS, blended_pairs, per_stage),
         "e2e": {"value": e2e_value, "unit": "Mviews/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 35 * 4 + HEIGHT * WIDTH * 4, "d2h_bytes_per_step": 4,
-                "api": "render_chn() + distillation loss + backward; camera + label map from pinned host memory; "
+                "h2d_bytes_per_step": 35 * 4 + HEIGHT * WIDTH * 4, "d2h_bytes_per_step": 8,
+                "api": "render_chn() + semantic.distill_loss_and_grad() + backward; camera + label map from pinned host memory; "
                        "loss read back every step (async 4-byte copy to pinned memory, consumed one step later)"},
         "gpu_launches": int(launches1[0] - launches0[0]), "cub_calls": int(launches1[1] - launches0[1]),
         "clocks": clocks,

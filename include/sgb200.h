@@ -216,6 +216,12 @@ int sgb_fusion_normalize(int32_t P, int32_t C, float* feat_sum, float* count, vo
  *
  * sgb_label_argmax: label[p] = argmax_{first_class <= k < K} planes[k][p] - first_class
  * (rendering[1:].argmax(dim=0), eval_segmentation.py:144). */
+/* Distillation loss of a rendered feature image against per-pixel class embeddings and its gradient, one pass:
+ *     loss = -(1 / (C N)) sum_p <render[:, p], class_emb[label(p)]>,   dL_drender[c][p] = -class_emb[label(p)][c] / (C N)
+ * render / dL_drender (C, N) planar fp32, class_emb (K, C), labels (N) int32 or int64 (clamped to [0, K)),
+ * loss: one double on the device (zeroed by the call). */
+int sgb_distill_loss(int32_t C, int32_t K, int64_t N, const float* render, const float* class_emb, const void* labels,
+                     int32_t labels_are_int64, float* dL_drender, double* loss, void* stream);
 int sgb_semantic_head(sgb_ctx* ctx, int32_t C, int32_t K, int64_t N, const float* render, const float* text,
                       int32_t first_class, float* sim, int64_t* label, void* stream);
 int sgb_feature_logits(int32_t P, int32_t C, int32_t K, int32_t Kpad, const float* features, const float* text,

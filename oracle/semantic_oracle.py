@@ -28,3 +28,13 @@ def label_margin(sim: np.ndarray, first_class: int = 1):
     larger than the fp32 noise of the two implementations)."""
     s = np.sort(sim[first_class:], axis=0)
     return s[-1] - s[-2] if s.shape[0] > 1 else np.full(sim.shape[1:], np.inf, np.float32)
+
+
+def distill_loss_and_grad(rendering: np.ndarray, class_emb: np.ndarray, labels: np.ndarray):
+    """loss = -mean(rendering * class_emb[labels].transpose(2,0,1)); grad = d loss / d rendering  (float64 sums)."""
+    C = rendering.shape[0]
+    tgt = class_emb[labels.astype(np.int64)].transpose(2, 0, 1).astype(np.float64)          # (C,H,W)
+    n = float(C * labels.size)
+    loss = -(rendering.astype(np.float64) * tgt).sum() / n
+    grad = (-(tgt / n)).astype(np.float32)
+    return loss, grad

@@ -54,7 +54,7 @@ EXPORTS = (
     "sgb_forward_render", "sgb_backward", "sgb_mark_visible", "sgb_state_field", "sgb_fusion_map",
     "sgb_fusion_accumulate", "sgb_fusion_normalize", "sgb_profile_enable", "sgb_profile_read",
     "sgb_profile_num_stages", "sgb_profile_stage_name", "sgb_ctx_launch_count",
-    "sgb_ctx_set_feature_grad_event", "sgb_semantic_head", "sgb_feature_logits", "sgb_label_argmax", "sgb_ctx_view_stat", "sgb_knn_mean_dist2",
+    "sgb_ctx_set_feature_grad_event", "sgb_semantic_head", "sgb_feature_logits", "sgb_label_argmax", "sgb_ctx_view_stat", "sgb_knn_mean_dist2", "sgb_distill_loss",
 )
 
 _lib = None
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
         lib.sgb_ctx_set_feature_grad_event.argtypes = [vp, vp]
         lib.sgb_ctx_view_stat.argtypes = [vp, C.c_int]
         lib.sgb_knn_mean_dist2.argtypes = [vp, i32, vp, vp, vp]
+        lib.sgb_distill_loss.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp]
         lib.sgb_ctx_view_stat.restype = i64
         lib.sgb_semantic_head.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, vp, vp]
         lib.sgb_feature_logits.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]

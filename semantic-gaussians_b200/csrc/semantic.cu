@@ -321,6 +321,67 @@ __global__ void label_argmax_kernel(int K, int first_class, long long N, const f
     label[p] = (long long)(bk - first_class);
 }
 
+// Training counterpart of the head: open-vocabulary distillation loss of a rendered feature image against
+// per-pixel class embeddings,  L = -(1 / (C N)) sum_p <render[:, p], E[label(p)]>,  and its gradient
+// dL/drender[c][p] = -E[label(p)][c] / (C N), in ONE pass (render read once, gradient written once; the torch
+// formulation — index_select of the (C,K) table + dot — moves 1.5x the bytes in three kernels).  Thread = 4
+// consecutive pixels, the pre-scaled table sits transposed [C][K+1] in shared memory (odd pitch: lanes with
+// different labels hit different banks, equal labels broadcast).
+template <bool VEC, typename LabelT>
+__global__ void __launch_bounds__(256) distill_loss_kernel(int C, int K, long long N, const float* __restrict__ render,
+                                                           const float* __restrict__ emb, const LabelT* __restrict__ labels,
+                                                           float scale, float* __restrict__ dL, double* __restrict__ loss) {
+    extern __shared__ float Es[];  // [C][Kp]
+    const int Kp = K | 1;
+    for (int e = threadIdx.x; e < C * K; e += blockDim.x) {
+        const int k = e / C, c = e - k * C;  // coalesced read of emb (K,C)
+        Es[c * Kp + k] = __ldg(emb + e) * scale;
+    }
+    __syncthreads();
+    const long long p0 = VEC ? ((long long)blockIdx.x * 256 + threadIdx.x) * 4 : (long long)blockIdx.x * 1024 + threadIdx.x;
+    long long px[4];
+    int lab[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        px[i] = VEC ? p0 + i : p0 + (long long)i * 256;
+        long long l = px[i] < N ? (long long)labels[px[i]] : 0;
+        lab[i] = (int)min(max(l, 0ll), (long long)K - 1);  // out-of-range labels are clamped, never read out of bounds
+    }
+    float acc = 0.f;
+    if (px[0] < N) {
+#pragma unroll 4
+        for (int c = 0; c < C; c++) {
+            const float* row = Es + c * Kp;
+            const float e0 = row[lab[0]], e1 = row[lab[1]], e2 = row[lab[2]], e3 = row[lab[3]];
+            const size_t off = (size_t)c * N;
+            if (VEC) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(render + off + px[0]));
+                acc = fmaf(x.x, e0, fmaf(x.y, e1, fmaf(x.z, e2, fmaf(x.w, e3, acc))));
+                *reinterpret_cast<float4*>(dL + off + px[0]) = make_float4(e0, e1, e2, e3);
+            } else {
+                const float ev[4] = {e0, e1, e2, e3};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (px[i] < N) {
+                        acc = fmaf(__ldg(render + off + px[i]), ev[i], acc);
+                        dL[off + px[i]] = ev[i];
+                    }
+            }
+        }
+    }
+    double d = (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    __shared__ double wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        atomicAdd(loss, t);
+    }
+}
+
 template <int NK4>
 void launch_head_t(int C, int K, long long N, const float* render, const float* text, int first_class, float* sim,
                    long long* label, float* best_val, int k0, int multi, cudaStream_t s) {
@@ -420,6 +481,38 @@ static int launch_label_argmax(int K, int first_class, long long N, const float*
 using namespace sgb;
 
 extern "C" {
+
+int sgb_distill_loss(int32_t C, int32_t K, int64_t N, const float* render, const float* class_emb, const void* labels,
+                     int32_t labels_are_int64, float* dL_drender, double* loss, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (C <= 0 || K <= 0 || N < 0) { set_error("sgb_distill_loss: need C > 0, K > 0, N >= 0"); return SGB_E_INVALID; }
+    if (!loss) { set_error("sgb_distill_loss: null loss"); return SGB_E_INVALID; }
+    SGB_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), s));
+    if (N == 0) return SGB_OK;
+    if (!render || !class_emb || !labels || !dL_drender) { set_error("sgb_distill_loss: null argument"); return SGB_E_INVALID; }
+    const size_t smem = sizeof(float) * (size_t)C * (K | 1);
+    if (smem > 200 * 1024) { set_error("sgb_distill_loss: C x K = %d x %d does not fit shared memory", C, K); return SGB_E_INVALID; }
+    const float scale = (float)(-1.0 / ((double)C * (double)N));
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(render) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dL_drender) & 15) == 0);
+    const unsigned blocks = (unsigned)((N + 1023) / 1024);
+#define SGB_DISTILL(VECF, T)                                                                                          \
+    do {                                                                                                              \
+        static DeviceOnce once;                                                                                       \
+        if (once.first_use_on_device())                                                                               \
+            SGB_CUDA(cudaFuncSetAttribute(distill_loss_kernel<VECF, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          200 * 1024));                                                               \
+        distill_loss_kernel<VECF, T><<<blocks, 256, smem, s>>>(C, K, (long long)N, render, class_emb, (const T*)labels, \
+                                                               scale, dL_drender, loss);                              \
+    } while (0)
+    if (vec && labels_are_int64) SGB_DISTILL(true, long long);
+    else if (vec) SGB_DISTILL(true, int);
+    else if (labels_are_int64) SGB_DISTILL(false, long long);
+    else SGB_DISTILL(false, int);
+#undef SGB_DISTILL
+    SGB_LAUNCH_CHECK("distill_loss_kernel", 0, s);
+    return SGB_OK;
+}
 
 int sgb_semantic_head(sgb_ctx* ctx, int32_t C, int32_t K, int64_t N, const float* render, const float* text,
                       int32_t first_class, float* sim, int64_t* label, void* stream) {

@@ -92,6 +92,31 @@ def label_argmax(planes: torch.Tensor, num_classes: Optional[int] = None, first_
     return label
 
 
+def distill_loss_and_grad(rendering: torch.Tensor, class_emb: torch.Tensor, labels: torch.Tensor
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Open-vocabulary distillation loss of a rendered (C,H,W) feature image against per-pixel class embeddings,
+    and its gradient, in one pass over the image:
+
+        loss = -(rendering * class_emb[labels].permute(2, 0, 1)).mean()          # labels (H,W) int32/int64
+        grad = d loss / d rendering                                               # (C,H,W)
+
+    Returns (loss: 0-d float64 CUDA tensor, grad: (C,H,W) float32).  Use as ``rendering.backward(grad)``."""
+    r = _check(rendering.detach(), "rendering")
+    e = _check(class_emb, "class_emb").to(r.device)
+    if r.ndim != 3 or e.ndim != 2 or e.shape[1] != r.shape[0]:
+        raise ValueError("rendering must be (C,H,W) and class_emb (K,C)")
+    if not labels.is_cuda or labels.dtype not in (torch.int32, torch.int64) or labels.numel() != r.shape[1] * r.shape[2]:
+        raise ValueError("labels must be a CUDA int32/int64 tensor with H*W entries")
+    lab = labels.contiguous()
+    grad = torch.empty_like(r)
+    loss = torch.zeros((), dtype=torch.float64, device=r.device)
+    stream, _ = _stream_ctx(r)
+    _lib.check(_lib.load().sgb_distill_loss(r.shape[0], e.shape[0], r.shape[1] * r.shape[2], r.data_ptr(), e.data_ptr(),
+                                           lab.data_ptr(), int(lab.dtype == torch.int64), grad.data_ptr(),
+                                           loss.data_ptr(), stream), "sgb_distill_loss")
+    return loss, grad
+
+
 def render_semantic_labels(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, text_features: torch.Tensor,
                            features: Optional[torch.Tensor] = None, first_class: int = 1, scaling_modifier=1.0,
                            override_shape=None, foreground=None, world_rotate=None,

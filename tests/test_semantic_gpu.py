@@ -139,3 +139,22 @@ def test_logit_space_labels_match_feature_image_head():
     from semantic_gaussians_b200.semantic import feature_logits
     out2 = render_semantic_labels(v, pc, Pipe, bg, text, logits=feature_logits(feats, text, pad_to=4))
     assert torch.equal(out2["label"], out["label"]) and torch.equal(out2["logits"], out["logits"])
+
+
+@pytest.mark.parametrize("C,K,H,W,dtype", [(16, 5, 7, 9, torch.int64), (256, 21, 64, 96, torch.int32), (130, 33, 20, 16, torch.int64)])
+def test_distill_loss_and_grad(C, K, H, W, dtype):
+    from oracle import semantic_oracle as so
+    from semantic_gaussians_b200.semantic import distill_loss_and_grad
+    dev = torch.device("cuda:0")
+    r, t = _case(C, K, H, W, 5 * C + K)
+    lab = np.random.default_rng(C).integers(0, K, (H, W))
+    R = torch.from_numpy(r).to(dev).requires_grad_(True)
+    loss, grad = distill_loss_and_grad(R, torch.from_numpy(t).to(dev), torch.from_numpy(lab).to(dev).to(dtype))
+    oloss, ograd = so.distill_loss_and_grad(r, t, lab)
+    assert loss.dtype == torch.float64 and abs(float(loss) - oloss) <= 1e-5 * abs(oloss) + 1e-9
+    assert np.allclose(grad.cpu().numpy(), ograd, rtol=1e-6, atol=0)
+    # same thing through torch autograd (what the e2e bench arm used before)
+    tl = -(R * torch.from_numpy(t).to(dev)[torch.from_numpy(lab).to(dev)].permute(2, 0, 1)).mean()
+    tl.backward()
+    assert abs(float(tl) - float(loss)) <= 1e-4 * abs(float(tl)) + 1e-9
+    assert torch.allclose(R.grad, grad, rtol=1e-5, atol=1e-12)
