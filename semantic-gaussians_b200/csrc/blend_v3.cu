@@ -704,9 +704,14 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
     const bool rows16 = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0);
     const int woff = warp * 32 + lane;
 
-    // background term of the own pixel over all channels (backward.cu:527-529)
+    // background term of the own pixel over all channels (backward.cu:527-529).  With an all-zero background
+    // (the usual case) the term vanishes; skipping it saves a second full read of dL/dout (ncu: 4.6 GB read
+    // by this kernel against 2.1 GB of dL/dout).
+    int bg_nonzero = 0;
+    for (int ch = tid; ch < C; ch += kThreads) bg_nonzero |= (bg_color[ch] != 0.f);
+    bg_nonzero = __syncthreads_or(bg_nonzero);
     float bgdot = 0.f;
-    if (inside)
+    if (inside && bg_nonzero)
         for (int ch = 0; ch < C; ch++) bgdot += bg_color[ch] * __ldg(dL_dpixels + (size_t)ch * plane + pix_id);
 
     const float T_final = inside ? final_Ts[pix_id] : 0.f;
