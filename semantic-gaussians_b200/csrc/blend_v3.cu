@@ -460,13 +460,16 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         for (int k = 0; k < MCH / 2; k++) acc[i][k] = make_float2(0.f, 0.f);
 
     const int woff = warp * 32 + pg * 8;
+    // Lane cg accumulates channels {4cg..4cg+3} and {32+4cg..32+4cg+3} of the slice: each of its two LDS.128 then
+    // reads 8 x 16 B that are contiguous across the 8 channel lanes (one 128-byte wavefront); the natural
+    // assignment 8cg..8cg+7 spread them over 256 B = two wavefronts per load.
     auto entry = [&](const Stage& sg, int e) {
         const float4 w0 = *reinterpret_cast<const float4*>(&sg.w[e][woff]);
         const float4 w1 = *reinterpret_cast<const float4*>(&sg.w[e][woff + 4]);
         float2 f[MCH / 2];
 #pragma unroll
         for (int q = 0; q < MCH / 4; q++) {
-            const float4 t = *reinterpret_cast<const float4*>(&sg.f[e][cg * MCH + 4 * q]);
+            const float4 t = *reinterpret_cast<const float4*>(&sg.f[e][q * 32 + cg * 4]);
             f[2 * q] = make_float2(t.x, t.y);
             f[2 * q + 1] = make_float2(t.z, t.w);
         }
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         const float Tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
         for (int k = 0; k < MCH; k++) {
-            const int chl = cg * MCH + k;
+            const int chl = (k >> 2) * 32 + cg * 4 + (k & 3);  // see `entry`: lane cg owns channels cg*4.. and 32+cg*4..
             if (chl >= nch) continue;
             const float bgc = bgS[chl];
             float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
@@ -767,12 +770,16 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
                 }
             }
         };
+        // An FT row holds the 64 entries of the segment PERMUTED: entries 8g..8g+3 of every entry group g first
+        // (32 floats), then entries 8g+4..8g+7 — so that each of a lane's two LDS.128 reads 8 x 16 B contiguous
+        // across the 8 entry-group lanes (one wavefront instead of two).
         auto fstore = [&](int buf) {
             const int e = tid >> 2, q = tid & 3;
-            FT[buf][q * 4 + 0][e] = fpre.x;
-            FT[buf][q * 4 + 1][e] = fpre.y;
-            FT[buf][q * 4 + 2][e] = fpre.z;
-            FT[buf][q * 4 + 3][e] = fpre.w;
+            const int pos = ((e >> 3) << 2) | (e & 3) | (((e >> 2) & 1) << 5);
+            FT[buf][q * 4 + 0][pos] = fpre.x;
+            FT[buf][q * 4 + 1][pos] = fpre.y;
+            FT[buf][q * 4 + 2][pos] = fpre.z;
+            FT[buf][q * 4 + 3][pos] = fpre.w;
         };
         // dL slab [CK ch][32 px of this warp]: 4 x cp.async(16 B) per lane, private to the warp
         auto dissue = [&](int sl, int buf) {
@@ -809,8 +816,8 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
             for (int k = 0; k < CK; k++) {
                 const float4 d0 = *reinterpret_cast<const float4*>(&DS[warp][buf][k][pg * 8]);
                 const float4 d1 = *reinterpret_cast<const float4*>(&DS[warp][buf][k][pg * 8 + 4]);
-                const float4 f0 = *reinterpret_cast<const float4*>(&FT[buf][k][eg * 8]);
-                const float4 f1 = *reinterpret_cast<const float4*>(&FT[buf][k][eg * 8 + 4]);
+                const float4 f0 = *reinterpret_cast<const float4*>(&FT[buf][k][eg * 4]);        // entries 8eg..8eg+3
+                const float4 f1 = *reinterpret_cast<const float4*>(&FT[buf][k][32 + eg * 4]);   // entries 8eg+4..8eg+7
                 const float2 ff[4] = {make_float2(f0.x, f0.y), make_float2(f0.z, f0.w), make_float2(f1.x, f1.y),
                                       make_float2(f1.z, f1.w)};
                 const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
