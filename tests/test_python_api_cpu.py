@@ -112,3 +112,32 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "liboracle" in txt or "libref_" in txt:
                     bad.append(f)
     assert not bad, f"product files reference the test oracle: {bad}"
+
+
+def test_next_row_modules_reject_cpu_tensors_loudly():
+    """semantic head / distCUDA2 / label rendering have no CPU path: CPU tensors raise, nothing falls back."""
+    import pytest
+    import torch
+    from semantic_gaussians_b200 import semantic
+    from semantic_gaussians_b200.simple_knn import distCUDA2
+    with pytest.raises(ValueError):
+        semantic.semantic_head(torch.zeros(4, 2, 2), torch.zeros(3, 4))
+    with pytest.raises(ValueError):
+        semantic.feature_logits(torch.zeros(5, 4), torch.zeros(3, 4))
+    with pytest.raises(ValueError):
+        semantic.label_argmax(torch.zeros(3, 2, 2))
+    with pytest.raises(ValueError):
+        semantic.distill_loss_and_grad(torch.zeros(4, 2, 2), torch.zeros(3, 4), torch.zeros(2, 2, dtype=torch.int64))
+    with pytest.raises(ValueError):
+        distCUDA2(torch.zeros(10, 3))
+
+
+def test_nccl_overlap_options_request_a_high_priority_stream(monkeypatch):
+    import torch.distributed as dist
+    if not hasattr(dist, "ProcessGroupNCCL"):
+        return
+    from semantic_gaussians_b200.distributed import nccl_overlap_options
+    monkeypatch.delenv("SGB_NCCL_MAX_CTAS", raising=False)
+    assert nccl_overlap_options().is_high_priority_stream
+    monkeypatch.setenv("SGB_NCCL_MAX_CTAS", "8")
+    assert nccl_overlap_options().config.max_ctas == 8
