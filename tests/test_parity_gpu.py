@@ -40,7 +40,8 @@ def _bits(t):
 
 
 @pytest.mark.parametrize("P,W,H,view", [(10000, 256, 256, 0), (200000, 640, 480, 2), (1000000, 1920, 1080, 1),
-                                        (30000, 333, 211, 3)])
+                                        (30000, 333, 211, 3),
+                                        (3000, 4112, 4112, 0)])   # 257 x 257 = 66 049 tiles: the 32-bit tile-key path
 def test_rgbd_forward_bit_exact_vs_reference(P, W, H, view):
     """K1 / K2: every integer stage, the state floats and the RGB-D pixels equal the reference's bits."""
     dev = torch.device("cuda:0")
@@ -272,3 +273,31 @@ def test_sh_degrees_and_ragged_image_sizes():
                         rotations=sc["rotations"], sh_degree=deg)
         assert torch.equal(_bits(o["color"]), _bits(out["color"])), (deg, W, H)
         assert torch.equal(_bits(o["depth"]), _bits(out["depth"]))
+
+
+def test_channel_forward_and_backward_above_65535_tiles():
+    """C > 4 path (alpha pass, directory, GEMM kernels) on a 66 049-tile image: tile ids no longer fit 16 bits."""
+    dev = torch.device("cuda:0")
+    C, W, H = 8, 4112, 4112
+    scene = make_scene(3000, seed=6, sh=False, channels=C)
+    cam = orbit_cameras(4, W, H)[2]
+    sc, cm = dev_scene(scene, dev, requires_grad=True), dev_cam(cam, dev)
+    bg = torch.linspace(0.0, 0.3, C, device=dev)
+    o = run_ours("chn", sc, cm, bg, use_features=True)
+    r = _ref("chn")
+    sd = {k: (v.detach() if v is not None else None) for k, v in sc.items()}
+    out = _ref_forward(r, sd, cm, C, True, bg)
+    assert torch.equal(o["radii"], out["radii"])
+    assert rel_err(o["color"], out["color"]) < 1e-5
+    dL = torch.zeros((C, H, W), device=dev)
+    dL[:, ::7, ::5] = 1.0
+    (o["color"] * dL).sum().backward()
+    g = sc["features"].grad
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    # linearity in the features pins the C-channel backward without a NUM_CHANNELS=8 reference build:
+    # d/df <render(f), dL> = render-weights, so <grad, f> == <render(f) - T*bg, dL>
+    with torch.no_grad():
+        o0 = run_ours("chn", {**sd, "features": torch.zeros_like(sd["features"])}, cm, bg, use_features=True)["color"]
+        lhs = float((g.double() * sd["features"].double()).sum())
+        rhs = float(((o["color"].detach() - o0).double() * dL.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-6
