@@ -91,6 +91,7 @@ def test_channel_forward_vs_reference(P, W, H, C):
     ("rgbd", 20000, 320, 240, 3, False),
     ("chn", 50000, 320, 240, 3, True),
     ("chn_c100", 50000, 320, 240, 100, True),  # reference rebuilt with NUM_CHANNELS=100
+    ("chn_c100", 30000, 333, 211, 100, True),  # ragged image (W % 4 = 1, partial tiles): scalar row paths of the GEMM kernels
     ("chn_c256", 100000, 640, 480, 256, True)])
 def test_backward_vs_reference(refname, P, W, H, C, use_features):
     dev = torch.device("cuda:0")
@@ -301,3 +302,41 @@ def test_channel_forward_and_backward_above_65535_tiles():
         lhs = float((g.double() * sd["features"].double()).sum())
         rhs = float(((o["color"].detach() - o0).double() * dL.double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-6
+
+
+@pytest.mark.parametrize("C,W,H", [(6, 250, 100), (5, 333, 211), (36, 641, 479)])
+def test_channel_counts_not_multiple_of_four_and_ragged_images(C, W, H):
+    """C % 4 != 0 takes the direct-load forward and the scalar feature loads of the chain backward; W % 4 != 0 the
+    scalar image-row paths.  Forward against the reference (any C), backward through linearity in the features."""
+    dev = torch.device("cuda:0")
+    scene = make_scene(20000, seed=8, sh=False, channels=C)
+    cam = orbit_cameras(4, W, H)[3]
+    sc, cm = dev_scene(scene, dev, requires_grad=True), dev_cam(cam, dev)
+    bg = torch.linspace(0.1, 0.4, C, device=dev)
+    o = run_ours("chn", sc, cm, bg, use_features=True)
+    sd = {k: (v.detach() if v is not None else None) for k, v in sc.items()}
+    out = _ref_forward(_ref("chn"), sd, cm, C, True, bg)
+    assert torch.equal(o["radii"], out["radii"])
+    assert frac_bad(o["color"], out["color"], rtol=RTOL, atol_scale=1e-6) == 0.0
+    dL = torch.as_tensor(np.random.default_rng(C).standard_normal((C, H, W)).astype(np.float32), device=dev)
+    (o["color"] * dL).sum().backward()
+    g = sc["features"].grad
+    with torch.no_grad():
+        o0 = run_ours("chn", {**sd, "features": torch.zeros_like(sd["features"])}, cm, bg, use_features=True)["color"]
+        lhs = float((g.double() * sd["features"].double()).sum())
+        rhs = float(((o["color"].detach() - o0).double() * dL.double()).sum())
+        assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-5
+    # every gradient must equal the one of the same problem zero-padded to a multiple of 4 channels (the vector
+    # paths, pinned against the reference's NUM_CHANNELS rebuilds above)
+    Cp = (C + 3) // 4 * 4 + 4
+    pad = lambda t, dim: torch.cat([t, torch.zeros(*[(Cp - C) if i == dim else n for i, n in enumerate(t.shape)], device=dev)], dim=dim)
+    sp = {k: (v.detach().clone().requires_grad_(True) if v is not None else None) for k, v in sc.items()}
+    sp["features"] = pad(sd["features"], 1).requires_grad_(True)
+    op_ = run_ours("chn", sp, cm, pad(bg, 0), use_features=True)
+    (op_["color"] * pad(dL, 0)).sum().backward()
+    assert frac_bad(op_["color"][:C], o["color"], rtol=RTOL, atol_scale=1e-6) == 0.0
+    for name in ("means3D", "scales", "rotations", "opacities"):
+        assert frac_bad(sc[name].grad, sp[name].grad, rtol=RTOL, atol_scale=1e-4) == 0.0, name
+    assert frac_bad(o["means2D"].grad, op_["means2D"].grad, rtol=RTOL, atol_scale=1e-4) == 0.0
+    assert frac_bad(g, sp["features"].grad[:, :C], rtol=RTOL, atol_scale=1e-4) == 0.0
+    assert float(sp["features"].grad[:, C:].abs().max()) == 0.0      # zero dL/dout on the padding channels
