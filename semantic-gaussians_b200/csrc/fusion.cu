@@ -137,6 +137,32 @@ __device__ __forceinline__ float to_f32(__half h) { return __half2float(h); }
 __device__ __forceinline__ float to_f32(float f) { return f; }
 
 // One warp per Gaussian (grid-stride): feat_sum[g, :] += featT[pix(g), :] for visible g.
+// fp16 maps: 64 channels x 64 pixels per CTA, every global access is a 4-byte pair (128 B per warp row instead
+// of the 64 B of the element-wise kernel above).  Shared cell (r, j) = the pixel pair (2j, 2j+1) of channel r.
+// Requires even npix and C and 4-byte aligned bases.
+__global__ void __launch_bounds__(256) transpose_half2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                                              int C, int npix) {
+    __shared__ uint32_t tile[64][33];
+    const int px0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 64; r += 8) {
+        const int c = c0 + r, px = px0 + 2 * tx;
+        uint32_t v = 0u;
+        if (c < C && px < npix) v = __ldg(reinterpret_cast<const uint32_t*>(in + (size_t)c * npix + px));
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    const int c = c0 + 2 * tx;
+    if (c >= C) return;
+    for (int r = ty; r < 64; r += 8) {
+        const int px = px0 + r;
+        if (px >= npix) break;
+        const uint32_t a = tile[2 * tx][r >> 1], b = tile[2 * tx + 1][r >> 1];
+        const uint32_t lo = (r & 1) ? (a >> 16) : (a & 0xFFFFu), hi = (r & 1) ? (b >> 16) : (b & 0xFFFFu);
+        *reinterpret_cast<uint32_t*>(out + (size_t)px * C + c) = lo | (hi << 16);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) fusion_gather_kernel(int P, int C, const int* __restrict__ pix_of,
                                                             const T* __restrict__ featT,
@@ -260,7 +286,12 @@ extern "C" int sgb_fusion_accumulate(sgb_ctx* ctx, const sgb_fusion_view* v, con
     const int gblocks = 148 * 8;
     {
         StageTimer t(ctx, ST_FUSION_TRANSPOSE, s);
-        if (feat_dtype == SGB_FEAT_F16)
+        const bool pairs = feat_dtype == SGB_FEAT_F16 && (npix % 2 == 0) && (C % 2 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(features) & 3) == 0) && ((reinterpret_cast<uintptr_t>(featT) & 3) == 0);
+        if (pairs)
+            transpose_half2_kernel<<<dim3((unsigned)((npix + 63) / 64), (unsigned)((C + 63) / 64)), tblock, 0, s>>>(
+                (const __half*)features, (__half*)featT, C, (int)npix);
+        else if (feat_dtype == SGB_FEAT_F16)
             transpose_kernel<__half><<<tgrid, tblock, 0, s>>>((const __half*)features, (__half*)featT, C, (int)npix);
         else
             transpose_kernel<float><<<tgrid, tblock, 0, s>>>((const float*)features, (float*)featT, C, (int)npix);
