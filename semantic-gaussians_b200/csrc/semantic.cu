@@ -253,56 +253,85 @@ __global__ void __launch_bounds__(kTmaThreads, 1) semantic_head_tma_kernel(
 }
 
 // Per-Gaussian similarities  out[p][k] = sum_c features[p][c] * text[k][c]  (einsum "cq,dq->dc"),
-// written with a row pitch of Kpad floats, columns K..Kpad-1 zero.  One warp per Gaussian row:
-// lanes stride over the channels (coalesced 512-byte pieces), class embeddings in shared memory.
-template <int KC>
+// written with a row pitch of Kpad floats, columns K..Kpad-1 zero.  Thread = two Gaussian rows, walked with
+// 16-byte loads (a row's 128-byte lines stay in L1 between iterations, so DRAM sees every line once); the
+// class embeddings sit transposed [C][KC] in shared memory and are read as broadcast LDS.128, 2 x KC register
+// accumulators, no cross-lane reduction.  (The first version — warp per row, butterfly reduction of every
+// class — spent most of its issue slots on SHFL/FADD and ran at 0.85 TB/s.)
+template <int NK4>
 __global__ void __launch_bounds__(256) feature_logits_kernel(int P, int C, int K, int Kpad, int k0,
                                                              const float* __restrict__ features,
                                                              const float* __restrict__ text, float* __restrict__ out) {
-    extern __shared__ __align__(16) float Tk[];  // [KC][Cp], Cp = C rounded up to 4, zero padded
+    constexpr int KC = NK4 * 4;
+    extern __shared__ __align__(16) float Ts[];  // [Cp][KC], Cp = C rounded up to 4, zero padded
     const int Cp = (C + 3) & ~3;
-    const int kc = min(KC, K - k0);
-    for (int e = threadIdx.x; e < KC * Cp; e += blockDim.x) {
-        const int k = e / Cp, c = e - k * Cp;
-        Tk[e] = (k < kc && c < C) ? __ldg(text + (size_t)(k0 + k) * C + c) : 0.f;
+    const int kc = min(KC, K - k0);              // real classes in this pass (may be <= 0 for a pure padding pass)
+    for (int e = threadIdx.x; e < Cp * KC; e += blockDim.x) {
+        const int c = e / KC, k = e - c * KC;
+        Ts[e] = (c < C && k < kc) ? __ldg(text + (size_t)(k0 + k) * C + c) : 0.f;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
     const bool vec = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(features) & 15) == 0);
-    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
-        float acc[KC];
+    const int cols = min(KC, Kpad - k0);         // columns this pass writes (classes + zero padding)
+    const bool vout = (Kpad & 3) == 0 && (k0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (long long p0 = 2ll * (blockIdx.x * blockDim.x + threadIdx.x); p0 < P; p0 += 2ll * gridDim.x * blockDim.x) {
+        const bool two = p0 + 1 < P;
+        const float* r0 = features + (size_t)p0 * C;
+        const float* r1 = two ? r0 + C : r0;
+        float a0[KC], a1[KC];
 #pragma unroll
-        for (int k = 0; k < KC; k++) acc[k] = 0.f;
-        const float* row = features + (size_t)p * C;
-        for (int c = lane * 4; c < Cp; c += 128) {
-            float4 f;
-            if (vec) f = __ldg(reinterpret_cast<const float4*>(row + c));
-            else {
-                f.x = c < C ? __ldg(row + c) : 0.f;
-                f.y = c + 1 < C ? __ldg(row + c + 1) : 0.f;
-                f.z = c + 2 < C ? __ldg(row + c + 2) : 0.f;
-                f.w = c + 3 < C ? __ldg(row + c + 3) : 0.f;
+        for (int k = 0; k < KC; k++) { a0[k] = 0.f; a1[k] = 0.f; }
+#pragma unroll 2
+        for (int c = 0; c < Cp; c += 4) {
+            float f0[4], f1[4];
+            if (vec) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(r0 + c));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(r1 + c));
+                f0[0] = v0.x; f0[1] = v0.y; f0[2] = v0.z; f0[3] = v0.w;
+                f1[0] = v1.x; f1[1] = v1.y; f1[2] = v1.z; f1[3] = v1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    f0[j] = c + j < C ? __ldg(r0 + c + j) : 0.f;
+                    f1[j] = c + j < C ? __ldg(r1 + c + j) : 0.f;
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float* trow = Ts + (size_t)(c + j) * KC;
+#pragma unroll
+                for (int q = 0; q < NK4; q++) {
+                    const float4 t = *reinterpret_cast<const float4*>(trow + 4 * q);
+                    a0[4 * q + 0] = fmaf(f0[j], t.x, a0[4 * q + 0]);
+                    a0[4 * q + 1] = fmaf(f0[j], t.y, a0[4 * q + 1]);
+                    a0[4 * q + 2] = fmaf(f0[j], t.z, a0[4 * q + 2]);
+                    a0[4 * q + 3] = fmaf(f0[j], t.w, a0[4 * q + 3]);
+                    a1[4 * q + 0] = fmaf(f1[j], t.x, a1[4 * q + 0]);
+                    a1[4 * q + 1] = fmaf(f1[j], t.y, a1[4 * q + 1]);
+                    a1[4 * q + 2] = fmaf(f1[j], t.z, a1[4 * q + 2]);
+                    a1[4 * q + 3] = fmaf(f1[j], t.w, a1[4 * q + 3]);
+                }
+            }
+        }
+        // padding columns (k >= kc) accumulated zeros: the embedding table is zero there
+        float* o0 = out + (size_t)p0 * Kpad + k0;
+        float* o1 = o0 + Kpad;
+        if (vout) {
+#pragma unroll
+            for (int q = 0; q < NK4; q++) {
+                if (4 * q >= cols) break;
+                *reinterpret_cast<float4*>(o0 + 4 * q) = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
+                if (two)
+                    *reinterpret_cast<float4*>(o1 + 4 * q) = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+            }
+        } else {
 #pragma unroll
             for (int k = 0; k < KC; k++) {
-                const float4 t = *reinterpret_cast<const float4*>(&Tk[k * Cp + c]);
-                acc[k] = fmaf(f.x, t.x, acc[k]);
-                acc[k] = fmaf(f.y, t.y, acc[k]);
-                acc[k] = fmaf(f.z, t.z, acc[k]);
-                acc[k] = fmaf(f.w, t.w, acc[k]);
+                if (k >= cols) break;
+                o0[k] = a0[k];
+                if (two) o1[k] = a1[k];
             }
         }
-        // transpose-reduce: after the butterfly every lane holds all sums; lane k stores class k
-        float mine = 0.f;
-#pragma unroll
-        for (int k = 0; k < KC; k++) {
-            float v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == k) mine = v;
-        }
-        if (lane < KC && k0 + lane < Kpad) out[(size_t)p * Kpad + k0 + lane] = lane < kc ? mine : 0.f;  // pad columns = 0
     }
 }
 
@@ -437,21 +466,21 @@ static int launch_semantic_head(sgb_ctx* ctx, int C, int K, long long N, const f
     return SGB_OK;
 }
 
-template <int KC>
+template <int NK4>
 static int launch_logits_t(int P, int C, int K, int Kpad, int k0, const float* features, const float* text, float* out,
                            cudaStream_t s) {
     const int Cp = (C + 3) & ~3;
-    const size_t smem = sizeof(float) * (size_t)KC * Cp;
+    const size_t smem = sizeof(float) * (size_t)NK4 * 4 * Cp;
     if (smem > 200 * 1024) {
         set_error("sgb_feature_logits: C = %d too large (class embeddings must fit shared memory)", C);
         return SGB_E_INVALID;
     }
     static DeviceOnce attr_set;
     if (attr_set.first_use_on_device()) {
-        SGB_CUDA(cudaFuncSetAttribute(feature_logits_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SGB_CUDA(cudaFuncSetAttribute(feature_logits_kernel<NK4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    const int blocks = min((P + 7) / 8, 148 * 4);
-    feature_logits_kernel<KC><<<blocks, 256, smem, s>>>(P, C, K, Kpad, k0, features, text, out);
+    const int blocks = min((P + 511) / 512, 148 * 8);
+    feature_logits_kernel<NK4><<<blocks, 256, smem, s>>>(P, C, K, Kpad, k0, features, text, out);
     SGB_LAUNCH_CHECK("feature_logits_kernel", 0, s);
     return SGB_OK;
 }
@@ -461,10 +490,10 @@ static int launch_feature_logits(int P, int C, int K, int Kpad, const float* fea
     for (int k0 = 0; k0 < Kpad; k0 += 32) {
         const int span = min(32, Kpad - k0);  // columns this pass writes (classes + zero padding)
         int rc;
-        if (span <= 8) rc = launch_logits_t<8>(P, C, K, Kpad, k0, features, text, out, s);
-        else if (span <= 16) rc = launch_logits_t<16>(P, C, K, Kpad, k0, features, text, out, s);
-        else if (span <= 24) rc = launch_logits_t<24>(P, C, K, Kpad, k0, features, text, out, s);
-        else rc = launch_logits_t<32>(P, C, K, Kpad, k0, features, text, out, s);
+        if (span <= 8) rc = launch_logits_t<2>(P, C, K, Kpad, k0, features, text, out, s);
+        else if (span <= 16) rc = launch_logits_t<4>(P, C, K, Kpad, k0, features, text, out, s);
+        else if (span <= 24) rc = launch_logits_t<6>(P, C, K, Kpad, k0, features, text, out, s);
+        else rc = launch_logits_t<8>(P, C, K, Kpad, k0, features, text, out, s);
         if (rc) return rc;
     }
     return SGB_OK;
