@@ -151,6 +151,53 @@ int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered,
                  const void* image_state, const float* dL_dpix /* [C,H,W] */,
                  const sgb_view_grads* grads, void* stream);
 
+/* ---- batched views (SURVEY.md §8 row n2 / BASELINE config K4): V views of the SAME Gaussians in one call.
+ *
+ * The reference renders one view per call in a Python loop (eval_segmentation.py:146-157, fusion.py:58-64,106-144);
+ * a view-sharded training / evaluation step renders a batch of views per GPU (K4: 32 views over 8 GPUs = 4 each).
+ * `in` carries everything the views share (sizes, Gaussian arrays, background, flags); its camera fields are
+ * ignored and replaced by cams[v].  Per view the results are IDENTICAL to V single-view calls; what the batch
+ * removes is per-view overhead:
+ *   - sgb_forward_geometry_batch enqueues the V projection / depth-order / scan sequences back to back and
+ *     synchronises the stream ONCE for all V instance counts (the single-view call synchronises per view);
+ *   - sgb_forward_render_batch enqueues binning, alpha pass and blend of all V views and synchronises ONCE for
+ *     the V weight-pool checks; every view keeps its own weight-pool slot inside the ctx (V <= SGB_MAX_BATCH),
+ *     so sgb_backward_batch reuses the rows of all V forwards;
+ *   - sgb_backward_batch accumulates: grads[v].dL_dcolors may be THE SAME (P, C) buffer for every view — the
+ *     per-Gaussian feature gradient is summed over the local views in place (one zero-fill, no V x (P, C)
+ *     temporaries, no V-way add), which is what a data-parallel step exchanges.  All V dL/dfeature kernels run
+ *     first, then the feature-gradient event (sgb_ctx_set_feature_grad_event) is recorded, then the V chain /
+ *     geometry kernels: the exchange of the big gradient overlaps the rest of the whole batch.  The small
+ *     per-Gaussian gradients (means2D, conic, opacity, means3D, cov3D, scales, rotations, sh) are per view
+ *     (distinct buffers per grads[v]; viewspace gradients feed per-view densification statistics).
+ */
+#define SGB_MAX_BATCH 8
+
+typedef struct sgb_camera {
+    const float* viewmatrix;     /* [16] device */
+    const float* projmatrix;     /* [16] device */
+    const float* campos;         /* [3]  device */
+    float tan_fovx, tan_fovy;
+} sgb_camera;
+
+int sgb_forward_geometry_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                               void* const* geometry_states, int32_t* const* radii,
+                               int64_t* num_rendered_host /* [V] */, void* stream);
+int sgb_forward_render_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                             const int64_t* num_rendered /* [V] host */, void* const* geometry_states,
+                             void* const* binning_states, void* const* image_states,
+                             const int32_t* const* radii, float* const* out_colors,
+                             float* const* out_depths /* NULL or [V] (C <= 4 only) */, void* stream);
+int sgb_backward_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                       const int64_t* num_rendered, const int32_t* const* radii,
+                       const void* const* geometry_states, const void* const* binning_states,
+                       const void* const* image_states, const float* const* dL_dpix,
+                       const sgb_view_grads* grads /* [V] */, void* stream);
+
+/* Identity of the build: "<version> src:<sha256 prefix of csrc/ + include/>" (set by build.py; bench.py prints
+ * it so that a stale prebuilt library cannot be mistaken for the sources next to it). */
+const char* sgb_build_id(void);
+
 /* rasterizer_impl.cu:54-66,141-153: present[i] = (view-space z > 0.2). present is uint8 [P]. */
 int sgb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
@@ -217,9 +264,11 @@ int sgb_fusion_normalize(int32_t P, int32_t C, float* feat_sum, float* count, vo
  * sgb_label_argmax: label[p] = argmax_{first_class <= k < K} planes[k][p] - first_class
  * (rendering[1:].argmax(dim=0), eval_segmentation.py:144). */
 /* Distillation loss of a rendered feature image against per-pixel class embeddings and its gradient, one pass:
- *     loss = -(1 / (C N)) sum_p <render[:, p], class_emb[label(p)]>,   dL_drender[c][p] = -class_emb[label(p)][c] / (C N)
- * render / dL_drender (C, N) planar fp32, class_emb (K, C), labels (N) int32 or int64 (clamped to [0, K)),
- * loss: one double on the device (zeroed by the call). */
+ *     loss = -(1 / (C Nv)) sum_p <render[:, p], class_emb[label(p)]>,   dL_drender[c][p] = -class_emb[label(p)][c] / (C Nv)
+ * render / dL_drender (C, N) planar fp32, class_emb (K, C), labels (N) int32 or int64.  A label outside [0, K)
+ * (e.g. -1 / 255 "unannotated") marks an IGNORED pixel: zero gradient, no loss term, not counted in the normaliser
+ * Nv = number of valid pixels (Nv = N when every label is in range).
+ * loss: TWO doubles on the device (zeroed by the call): [0] the loss, [1] Nv. */
 int sgb_distill_loss(int32_t C, int32_t K, int64_t N, const float* render, const float* class_emb, const void* labels,
                      int32_t labels_are_int64, float* dL_drender, double* loss, void* stream);
 int sgb_semantic_head(sgb_ctx* ctx, int32_t C, int32_t K, int64_t N, const float* render, const float* text,

@@ -28,7 +28,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference/submodules"
 REF_OUT = os.path.join(HERE, "_ref")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CHN_BWD_VARIANTS = (100, 256)   # libref_chn_c100.so, libref_chn_c256.so
+CHN_BWD_VARIANTS = (100, 256, 512)   # libref_chn_c100.so, libref_chn_c256.so, libref_chn_c512.so (K4)
 
 
 def _newer(target: str, sources) -> bool:

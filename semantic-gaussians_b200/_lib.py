@@ -39,6 +39,15 @@ class ViewGrads(C.Structure):
         "dL_dsh", "dL_dscales", "dL_drotations")]
 
 
+class Camera(C.Structure):
+    """sgb_camera: the per-view fields of a batched call."""
+    _fields_ = [("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float)]
+
+
+MAX_BATCH = 8
+
+
 class FusionView(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("xyz", C.c_void_p), ("world_to_camera", C.c_void_p),
@@ -55,6 +64,7 @@ EXPORTS = (
     "sgb_fusion_accumulate", "sgb_fusion_normalize", "sgb_profile_enable", "sgb_profile_read",
     "sgb_profile_num_stages", "sgb_profile_stage_name", "sgb_ctx_launch_count",
     "sgb_ctx_set_feature_grad_event", "sgb_semantic_head", "sgb_feature_logits", "sgb_label_argmax", "sgb_ctx_view_stat", "sgb_knn_mean_dist2", "sgb_distill_loss",
+    "sgb_forward_geometry_batch", "sgb_forward_render_batch", "sgb_backward_batch", "sgb_build_id",
 )
 
 _lib = None
@@ -92,6 +102,14 @@ def load() -> C.CDLL:
         lib.sgb_forward_render.argtypes = [vp, C.POINTER(ViewInputs), i64, vp, vp, vp, vp, vp, vp, vp]
         lib.sgb_backward.argtypes = [vp, C.POINTER(ViewInputs), i64, vp, vp, vp, vp, vp,
                                      C.POINTER(ViewGrads), vp]
+        pvp = C.POINTER(vp)
+        lib.sgb_forward_geometry_batch.argtypes = [vp, C.POINTER(ViewInputs), i32, C.POINTER(Camera), pvp, pvp,
+                                                   C.POINTER(i64), vp]
+        lib.sgb_forward_render_batch.argtypes = [vp, C.POINTER(ViewInputs), i32, C.POINTER(Camera), C.POINTER(i64),
+                                                 pvp, pvp, pvp, pvp, pvp, pvp, vp]
+        lib.sgb_backward_batch.argtypes = [vp, C.POINTER(ViewInputs), i32, C.POINTER(Camera), C.POINTER(i64), pvp,
+                                           pvp, pvp, pvp, pvp, C.POINTER(ViewGrads), vp]
+        lib.sgb_build_id.restype = C.c_char_p
         lib.sgb_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
         lib.sgb_state_field.argtypes = [C.c_char_p, i32, i64, i32, i32, vp, vp, vp, vp, vp]
         lib.sgb_state_field.restype = i64
@@ -159,6 +177,11 @@ def set_feature_grad_event(ctx: int, cuda_event) -> None:
 def view_stat(ctx: int, which: int) -> int:
     """0: blended (pixel, Gaussian) pairs of the last C > 4 view; 1: weight-row chunks in use."""
     return int(load().sgb_ctx_view_stat(ctx, which))
+
+
+def build_id() -> str:
+    """Identity string baked into the loaded library (version + hash of the sources it was built from)."""
+    return load().sgb_build_id().decode()
 
 
 def launch_count(ctx: int) -> tuple:

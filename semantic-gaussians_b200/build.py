@@ -16,6 +16,19 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+def source_hash() -> str:
+    """sha256 over csrc/* and include/sgb200.h (sorted by name): the identity baked into the library as
+    sgb_build_id() and recomputed by bench.py, so a stale prebuilt .so cannot pass for the sources next to it."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "sgb200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     d.append(os.path.join(os.path.dirname(HERE), "include", "sgb200.h"))
@@ -34,6 +47,8 @@ def build(verbose: bool = False, force: bool = False, ptxas_verbose: bool = Fals
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "api.cu":
+            cmd.append(f'-DSGB_BUILD_ID="{source_hash()}"')
         if ptxas_verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -72,14 +72,23 @@ using namespace sgb;
 extern "C" {
 
 const char* sgb_last_error(void) { return g_err; }
-const char* sgb_version(void) { return "sgb200 0.1.0 (sm_100a)"; }
+const char* sgb_version(void) { return "sgb200 0.2.0 (sm_100a)"; }
+#ifndef SGB_BUILD_ID
+#define SGB_BUILD_ID "unknown"
+#endif
+const char* sgb_build_id(void) { return "sgb200 0.2.0 src:" SGB_BUILD_ID; }
 
 int sgb_ctx_create(sgb_ctx** out, int device) {
     if (!out) { set_error("null out"); return SGB_E_INVALID; }
+    // the caller's current device is left as it was (a host framework tracks it; changing it behind its back makes
+    // later launches land on streams of a non-current device)
+    int prev = -1;
+    SGB_CUDA(cudaGetDevice(&prev));
     SGB_CUDA(cudaSetDevice(device));
     sgb_ctx* c = new sgb_ctx();
     c->device = device;
-    cudaError_t e = cudaMallocHost(&c->pinned, 64);
+    cudaError_t e = cudaMallocHost(&c->pinned, 1024);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMallocHost"); }
     *out = c;
     return SGB_OK;
@@ -96,7 +105,8 @@ void sgb_ctx_destroy(sgb_ctx* c) {
     if (c->geom.p) cudaFree(c->geom.p);
     if (c->bin.p) cudaFree(c->bin.p);
     if (c->misc.p) cudaFree(c->misc.p);
-    if (c->pool.p) cudaFree(c->pool.p);
+    for (PoolSlot& sl : c->pools)
+        if (sl.mem.p) cudaFree(sl.mem.p);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -144,39 +154,207 @@ uint64_t sgb_ctx_launch_count(const sgb_ctx* c, int library_calls) {
     return c ? (library_calls ? c->lib_launches : c->launches) : 0;
 }
 
-size_t sgb_ctx_scratch_bytes(const sgb_ctx* c) { return c ? c->geom.cap + c->bin.cap + c->misc.cap + c->pool.cap : 0; }
+size_t sgb_ctx_scratch_bytes(const sgb_ctx* c) {
+    if (!c) return 0;
+    size_t n = c->geom.cap + c->bin.cap + c->misc.cap;
+    for (const PoolSlot& sl : c->pools) n += sl.mem.cap;
+    return n;
+}
 
 size_t sgb_geometry_bytes(int32_t P) { return GeomView::carve(nullptr, P > 0 ? P : 1).bytes; }
 size_t sgb_binning_bytes(int64_t R) { return BinView::carve(nullptr, R).bytes; }
 size_t sgb_image_bytes(int32_t W, int32_t H) { return ImgView::carve(nullptr, W, H).bytes; }
 
+// ---- forward / backward, single view and batched (the single-view entry points are the V = 1 case) -----------
+static sgb_view_inputs with_camera(const sgb_view_inputs& in, const sgb_camera* cams, int v) {
+    sgb_view_inputs o = in;
+    if (cams) {
+        o.viewmatrix = cams[v].viewmatrix;
+        o.projmatrix = cams[v].projmatrix;
+        o.campos = cams[v].campos;
+        o.tan_fovx = cams[v].tan_fovx;
+        o.tan_fovy = cams[v].tan_fovy;
+    }
+    return o;
+}
+
+static int check_batch(const sgb_view_inputs* in, int32_t V, const sgb_camera* cams, sgb_view_inputs* probe) {
+    if (!in) { set_error("null sgb_view_inputs"); return SGB_E_INVALID; }
+    if (V < 1 || V > SGB_MAX_BATCH) { set_error("batch of %d views: need 1 <= V <= %d", V, SGB_MAX_BATCH); return SGB_E_INVALID; }
+    if (!cams) { set_error("null camera array"); return SGB_E_INVALID; }
+    for (int v = 0; v < V; v++) {
+        *probe = with_camera(*in, cams, v);
+        int rc = check_inputs(probe);
+        if (rc) return rc;
+    }
+    return SGB_OK;
+}
+
+static int forward_geometry_impl(sgb_ctx* ctx, const sgb_view_inputs& in, int V, const sgb_camera* cams,
+                                 void* const* geometry_states, int32_t* const* radii, int64_t* num_rendered_host,
+                                 cudaStream_t s) {
+    for (int v = 0; v < V; v++) num_rendered_host[v] = 0;
+    ctx->last_P = 0;
+    ctx->last_V = 0;
+    if (in.P == 0) return SGB_OK;  // rasterize_points.cu:84: nothing to do for an empty scene
+    int rc = run_depth_order_and_scan(ctx, in, V, cams, geometry_states, radii, num_rendered_host, s);
+    if (rc) return rc;
+    for (int v = 0; v < V; v++)
+        if (num_rendered_host[v] > 0x7fffffffLL) {
+            set_error("num_rendered %lld exceeds int32", (long long)num_rendered_host[v]);
+            return SGB_E_OVERFLOW;
+        }
+    return SGB_OK;
+}
+
+static int forward_render_impl(sgb_ctx* ctx, const sgb_view_inputs& in_common, int V, const sgb_camera* cams,
+                               const int64_t* num_rendered, void* const* geometry_states, void* const* binning_states,
+                               void* const* image_states, const int32_t* const* radii, float* const* out_colors,
+                               float* const* out_depths, cudaStream_t s) {
+    int64_t maxR = 0;
+    for (int v = 0; v < V; v++) maxR = num_rendered[v] > maxR ? num_rendered[v] : maxR;
+    int rc = reserve_binning(ctx, in_common, in_common.P > 0 ? maxR : 0, s);
+    if (rc) return rc;
+    bool pending[SGB_MAX_BATCH] = {};
+    auto enqueue_view = [&](int v, bool binning) -> int {
+        const sgb_view_inputs in = with_camera(in_common, cams, v);
+        const int64_t R = in.P > 0 ? num_rendered[v] : 0;
+        GeomView g = GeomView::carve(geometry_states[v], in.P > 0 ? in.P : 1);
+        BinView b = BinView::carve(binning_states[v], R);
+        ImgView im = ImgView::carve(image_states[v], in.W, in.H);
+        if (binning) {
+            int r = run_binning(ctx, in, v, R, g, b, im, radii[v], s);
+            if (r) return r;
+        }
+        const float* colors = in.colors_precomp ? in.colors_precomp : g.rgb;  // rasterizer_impl.cu:324
+        if (in.C > 4) {
+            pending[v] = true;
+            return blend_forward_v3_enqueue(ctx, v, in, R, g, b, im, colors, out_colors[v], s);
+        }
+        StageTimer t(ctx, ST_BLEND_FWD, s);
+        ctx->launches += 1;
+        return launch_blend_forward(in, g, b, im, colors, out_colors[v], out_depths ? out_depths[v] : nullptr, s);
+    };
+    for (int v = 0; v < V; v++) {
+        rc = enqueue_view(v, true);
+        if (rc) return rc;
+    }
+    if (in_common.C <= 4) return SGB_OK;
+    // one sync for the weight-pool checks of all views; an overflowed view (first view of a new scene) is redone
+    for (int attempt = 0; attempt < 4; attempt++) {
+        SGB_CUDA(cudaStreamSynchronize(s));
+        bool again = false;
+        for (int v = 0; v < V; v++) {
+            if (!pending[v]) continue;
+            const sgb_view_inputs in = with_camera(in_common, cams, v);
+            const int64_t R = in.P > 0 ? num_rendered[v] : 0;
+            BinView b = BinView::carve(binning_states[v], R);
+            const int f = blend_forward_v3_finish(ctx, v, in, R, b);
+            if (f < 0) return f;
+            if (f == 0) { pending[v] = false; continue; }
+            rc = enqueue_view(v, false);
+            if (rc) return rc;
+            again = true;
+        }
+        if (!again) return SGB_OK;
+    }
+    set_error("weight pool kept overflowing");
+    return SGB_E_NOMEM;
+}
+
+static int backward_impl(sgb_ctx* ctx, const sgb_view_inputs& in_common, int V, const sgb_camera* cams,
+                         const int64_t* num_rendered, const int32_t* const* radii, const void* const* geometry_states,
+                         const void* const* binning_states, const void* const* image_states,
+                         const float* const* dL_dpix, const sgb_view_grads* grads, cudaStream_t s) {
+    if (in_common.P == 0) {
+        if (ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
+        return SGB_OK;
+    }
+    struct View { sgb_view_inputs in; int64_t R; GeomView g; BinView b; ImgView im; const float* colors; };
+    View vw[SGB_MAX_BATCH];
+    for (int v = 0; v < V; v++) {
+        const sgb_view_grads& gr = grads[v];
+        if (!geometry_states[v] || !radii[v] || !image_states[v] || !dL_dpix[v] || !gr.dL_dmeans2D || !gr.dL_dconic ||
+            !gr.dL_dopacity || !gr.dL_dcolors || !gr.dL_dmeans3D || !gr.dL_dcov3D || (in_common.shs && !gr.dL_dsh) ||
+            (in_common.scales && (!gr.dL_dscales || !gr.dL_drotations))) {
+            set_error("sgb_backward: null state or gradient buffer");
+            return SGB_E_INVALID;
+        }
+        vw[v].in = with_camera(in_common, cams, v);
+        vw[v].R = num_rendered[v];
+        vw[v].g = GeomView::carve(const_cast<void*>(geometry_states[v]), in_common.P);
+        vw[v].b = BinView::carve(const_cast<void*>(binning_states[v]), num_rendered[v]);
+        vw[v].im = ImgView::carve(const_cast<void*>(image_states[v]), in_common.W, in_common.H);
+        vw[v].colors = in_common.colors_precomp ? in_common.colors_precomp : vw[v].g.rgb;  // rasterizer_impl.cu:394
+    }
+    const bool wide = in_common.C > 4;
+    int rc;
+    // dL/dfeature of every view first: it needs only the weight rows and dL/dout, it is the one large gradient and
+    // it accumulates across the views of a batch, so a data-parallel caller can start exchanging it while the
+    // chain / geometry kernels of the whole batch run (sgb200.h)
+    if (wide)
+        for (int v = 0; v < V; v++) {
+            if (vw[v].R <= 0) continue;
+            rc = blend_backward_v3_dfeature(ctx, vw[v].in, vw[v].R, vw[v].g, vw[v].b, vw[v].im, dL_dpix[v],
+                                            grads[v].dL_dcolors, s);
+            if (rc) return rc;
+        }
+    if (wide && ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
+    for (int v = 0; v < V; v++) {
+        const sgb_view_grads& gr = grads[v];
+        if (vw[v].R > 0 && wide) {
+            rc = blend_backward_v3_chain(ctx, vw[v].in, vw[v].R, vw[v].g, vw[v].b, vw[v].im, vw[v].colors, dL_dpix[v],
+                                         gr.dL_dmeans2D, gr.dL_dconic, gr.dL_dopacity, s);
+            if (rc) return rc;
+        } else if (vw[v].R > 0) {
+            StageTimer t(ctx, ST_BLEND_BWD, s);
+            ctx->launches += 1;
+            rc = launch_blend_backward(vw[v].in, vw[v].g, vw[v].b, vw[v].im, vw[v].colors, dL_dpix[v], gr.dL_dmeans2D,
+                                       gr.dL_dconic, gr.dL_dopacity, gr.dL_dcolors, s);
+            if (rc) return rc;
+        }
+        if (!wide && v == V - 1 && ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
+        const float* cov3D = in_common.cov3D_precomp ? in_common.cov3D_precomp : vw[v].g.cov3D;  // rasterizer_impl.cu:417
+        StageTimer t(ctx, ST_GEOM_BWD, s);
+        ctx->launches += 1;
+        rc = launch_geom_backward(vw[v].in, vw[v].g, radii[v], cov3D, gr.dL_dcolors, gr, s);
+        if (rc) return rc;
+    }
+    return SGB_OK;
+}
+
 int sgb_forward_geometry(sgb_ctx* ctx, const sgb_view_inputs* in, void* geometry_state, int32_t* radii,
                          int64_t* num_rendered_host, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
     int rc = check_inputs(in);
     if (rc) return rc;
     if (!ctx || !num_rendered_host || (in->P > 0 && (!geometry_state || !radii))) {
         set_error("sgb_forward_geometry: null ctx/state/radii/num_rendered");
         return SGB_E_INVALID;
     }
-    *num_rendered_host = 0;
-    ctx->last_P = 0;
-    ctx->pool_valid = false;  // a new view starts: cached weight rows belong to the previous one
-    if (in->P == 0) return SGB_OK;  // rasterize_points.cu:84: nothing to do for an empty scene
-    GeomView g = GeomView::carve(geometry_state, in->P);
-    rc = run_depth_order_and_scan(ctx, *in, g, radii, num_rendered_host, s);
+    void* gs[1] = {geometry_state};
+    int32_t* rd[1] = {radii};
+    return forward_geometry_impl(ctx, *in, 1, nullptr, gs, rd, num_rendered_host, (cudaStream_t)stream);
+}
+
+int sgb_forward_geometry_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                               void* const* geometry_states, int32_t* const* radii, int64_t* num_rendered_host,
+                               void* stream) {
+    sgb_view_inputs probe;
+    int rc = check_batch(in, V, cams, &probe);
     if (rc) return rc;
-    if (*num_rendered_host > 0x7fffffffLL) {
-        set_error("num_rendered %lld exceeds int32", (long long)*num_rendered_host);
-        return SGB_E_OVERFLOW;
+    if (!ctx || !num_rendered_host || !geometry_states || !radii) {
+        set_error("sgb_forward_geometry_batch: null ctx/state/radii/num_rendered");
+        return SGB_E_INVALID;
     }
-    return SGB_OK;
+    if (in->P > 0)
+        for (int v = 0; v < V; v++)
+            if (!geometry_states[v] || !radii[v]) { set_error("sgb_forward_geometry_batch: null state of view %d", v); return SGB_E_INVALID; }
+    return forward_geometry_impl(ctx, *in, V, cams, geometry_states, radii, num_rendered_host, (cudaStream_t)stream);
 }
 
 int sgb_forward_render(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, void* geometry_state,
                        void* binning_state, void* image_state, const int32_t* radii, float* out_color,
                        float* out_depth, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
     int rc = check_inputs(in);
     if (rc) return rc;
     if (!ctx || !image_state || !out_color || (in->P > 0 && (!geometry_state || !radii)) ||
@@ -184,63 +362,71 @@ int sgb_forward_render(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rend
         set_error("sgb_forward_render: null ctx/state/output");
         return SGB_E_INVALID;
     }
-    GeomView g = GeomView::carve(geometry_state, in->P > 0 ? in->P : 1);
-    BinView b = BinView::carve(binning_state, num_rendered);
-    ImgView im = ImgView::carve(image_state, in->W, in->H);
-    if (in->P == 0) num_rendered = 0;
-    rc = run_binning(ctx, *in, num_rendered, g, b, im, radii, s);
+    if (in->C > 4 && out_depth) {
+        set_error("out_depth is only produced by the 3-channel RGB-D path (C <= 4)");
+        return SGB_E_INVALID;
+    }
+    void* gs[1] = {geometry_state};
+    void* bs[1] = {binning_state};
+    void* is[1] = {image_state};
+    const int32_t* rd[1] = {radii};
+    float* oc[1] = {out_color};
+    float* od[1] = {out_depth};
+    return forward_render_impl(ctx, *in, 1, nullptr, &num_rendered, gs, bs, is, rd, oc, od, (cudaStream_t)stream);
+}
+
+int sgb_forward_render_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                             const int64_t* num_rendered, void* const* geometry_states, void* const* binning_states,
+                             void* const* image_states, const int32_t* const* radii, float* const* out_colors,
+                             float* const* out_depths, void* stream) {
+    sgb_view_inputs probe;
+    int rc = check_batch(in, V, cams, &probe);
     if (rc) return rc;
-    const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:324
-    if (in->C > 4) {
-        if (out_depth) {
-            set_error("out_depth is only produced by the 3-channel RGB-D path (C <= 4)");
+    if (!ctx || !num_rendered || !geometry_states || !binning_states || !image_states || !radii || !out_colors) {
+        set_error("sgb_forward_render_batch: null argument");
+        return SGB_E_INVALID;
+    }
+    if (in->C > 4 && out_depths) {
+        set_error("out_depth is only produced by the 3-channel RGB-D path (C <= 4)");
+        return SGB_E_INVALID;
+    }
+    for (int v = 0; v < V; v++)
+        if (!image_states[v] || !out_colors[v] || (in->P > 0 && (!geometry_states[v] || !radii[v])) ||
+            (num_rendered[v] > 0 && !binning_states[v])) {
+            set_error("sgb_forward_render_batch: null state/output of view %d", v);
             return SGB_E_INVALID;
         }
-        return blend_forward_v3(ctx, *in, num_rendered, g, b, im, colors, out_color, s);
-    }
-    StageTimer t(ctx, ST_BLEND_FWD, s);
-    ctx->launches += 1;
-    return launch_blend_forward(*in, g, b, im, colors, out_color, out_depth, s);
+    return forward_render_impl(ctx, *in, V, cams, num_rendered, geometry_states, binning_states, image_states, radii,
+                               out_colors, out_depths, (cudaStream_t)stream);
 }
 
 int sgb_backward(sgb_ctx* ctx, const sgb_view_inputs* in, int64_t num_rendered, const int32_t* radii,
                  const void* geometry_state, const void* binning_state, const void* image_state,
                  const float* dL_dpix, const sgb_view_grads* gr, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
     int rc = check_inputs(in);
     if (rc) return rc;
     if (!ctx || !gr || !dL_dpix || !image_state) { set_error("sgb_backward: null argument"); return SGB_E_INVALID; }
-    if (in->P == 0) {
-        if (ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
-        return SGB_OK;
-    }
-    if (!geometry_state || !radii || !gr->dL_dmeans2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolors ||
-        !gr->dL_dmeans3D || !gr->dL_dcov3D || (in->shs && !gr->dL_dsh) || (in->scales && (!gr->dL_dscales || !gr->dL_drotations))) {
-        set_error("sgb_backward: null state or gradient buffer");
+    const int32_t* rd[1] = {radii};
+    const void* gs[1] = {geometry_state};
+    const void* bs[1] = {binning_state};
+    const void* is[1] = {image_state};
+    const float* dl[1] = {dL_dpix};
+    return backward_impl(ctx, *in, 1, nullptr, &num_rendered, rd, gs, bs, is, dl, gr, (cudaStream_t)stream);
+}
+
+int sgb_backward_batch(sgb_ctx* ctx, const sgb_view_inputs* in, int32_t V, const sgb_camera* cams,
+                       const int64_t* num_rendered, const int32_t* const* radii, const void* const* geometry_states,
+                       const void* const* binning_states, const void* const* image_states,
+                       const float* const* dL_dpix, const sgb_view_grads* grads, void* stream) {
+    sgb_view_inputs probe;
+    int rc = check_batch(in, V, cams, &probe);
+    if (rc) return rc;
+    if (!ctx || !num_rendered || !radii || !geometry_states || !binning_states || !image_states || !dL_dpix || !grads) {
+        set_error("sgb_backward_batch: null argument");
         return SGB_E_INVALID;
     }
-    GeomView g = GeomView::carve(const_cast<void*>(geometry_state), in->P);
-    BinView b = BinView::carve(const_cast<void*>(binning_state), num_rendered);
-    ImgView im = ImgView::carve(const_cast<void*>(image_state), in->W, in->H);
-    const float* colors = in->colors_precomp ? in->colors_precomp : g.rgb;  // rasterizer_impl.cu:394
-    if (num_rendered > 0 && in->C > 4) {
-        rc = blend_backward_v3(ctx, *in, num_rendered, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic,
-                               gr->dL_dopacity, gr->dL_dcolors, s);
-        if (rc) return rc;
-    } else if (num_rendered > 0) {
-        StageTimer t(ctx, ST_BLEND_BWD, s);
-        ctx->launches += 1;
-        rc = launch_blend_backward(*in, g, b, im, colors, dL_dpix, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity,
-                                   gr->dL_dcolors, s);
-        if (rc) return rc;
-    }
-    // C > 4 records the event inside blend_backward_v3, right after the dL/dfeature kernel
-    if (ctx->feature_grad_event && !(num_rendered > 0 && in->C > 4))
-        SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
-    const float* cov3D = in->cov3D_precomp ? in->cov3D_precomp : g.cov3D;  // rasterizer_impl.cu:417
-    StageTimer t(ctx, ST_GEOM_BWD, s);
-    ctx->launches += 1;
-    return launch_geom_backward(*in, g, radii, cov3D, gr->dL_dcolors, *gr, s);
+    return backward_impl(ctx, *in, V, cams, num_rendered, radii, geometry_states, binning_states, image_states, dL_dpix,
+                         grads, (cudaStream_t)stream);
 }
 
 int64_t sgb_ctx_view_stat(const sgb_ctx* ctx, int which) {

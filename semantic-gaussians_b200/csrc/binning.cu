@@ -25,10 +25,22 @@ __global__ void iota_kernel(int P, uint32_t* v) {
 }
 
 // tiles_touched in depth order (input of the offsets scan)
+// Also sums the counts in 64 bits: the 32-bit scan below wraps silently once the instance count reaches 2^32,
+// and a wrapped (small) R would pass the int32 check in sgb_forward_geometry and let the emitter write past
+// the binning buffer.
 __global__ void gather_counts_kernel(int P, const uint32_t* __restrict__ perm,
-                                     const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ out) {
+                                     const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ out,
+                                     unsigned long long* __restrict__ total64) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) out[i] = tiles_touched[perm[i]];
+    uint32_t n = 0;
+    if (i < P) {
+        n = tiles_touched[perm[i]];
+        out[i] = n;
+    }
+    unsigned long long t = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(total64, t);
 }
 
 // One warp handles 32 consecutive slots of the depth order; for each visible Gaussian its lanes
@@ -129,63 +141,79 @@ int Scratch::ensure(size_t n) {
     return SGB_OK;
 }
 
-// preprocess -> depth order -> scan -> R (one stream sync, like rasterizer_impl.cu:283).
-int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g, int32_t* radii,
-                             int64_t* R_host, cudaStream_t s) {
-    const int P = in.P;
-    // scratch layout: keys_in | keys_out | vals_in | vals_out(perm) | offsets | cub temp
+// preprocess -> depth order -> scan -> R for V views (one stream sync for all of them; the reference blocks once
+// per view, rasterizer_impl.cu:283).
+int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in_common, int V, const sgb_camera* cams,
+                             void* const* geometry_states, int32_t* const* radii_v, int64_t* R_host, cudaStream_t s) {
+    const int P = in_common.P;
+    // scratch layout per view: keys_in | keys_out | vals_in | vals_out(perm) | offsets | cub temp | 64-bit total
     size_t sort_tmp = 0, scan_tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, P, 0, 32, s);
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, P, s);
-    size_t arr = align_up(sizeof(uint32_t) * (size_t)P);
-    size_t tmp = align_up(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
-    int rc = ctx->geom.ensure(5 * arr + tmp);
+    const size_t arr = align_up(sizeof(uint32_t) * (size_t)P);
+    const size_t tmp = align_up(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
+    const size_t per_view = 5 * arr + tmp + 256;
+    int rc = ctx->geom.ensure((size_t)V * per_view);
     if (rc) return rc;
-    char* base = (char*)ctx->geom.p;
-    uint32_t* keys_in = (uint32_t*)(base);
-    uint32_t* keys_out = (uint32_t*)(base + arr);
-    uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
-    uint32_t* perm = (uint32_t*)(base + 3 * arr);
-    uint32_t* offsets = (uint32_t*)(base + 4 * arr);
-    void* cub_tmp = base + 5 * arr;
-
-    {
-        StageTimer t(ctx, ST_PREPROCESS, s);
-        rc = launch_preprocess(in, g, radii, keys_in, s);
-        if (rc) return rc;
-        ctx->launches += 1;
+    unsigned long long* h = (unsigned long long*)ctx->pinned;
+    for (int v = 0; v < V; v++) {
+        sgb_view_inputs in = in_common;
+        if (cams) {
+            in.viewmatrix = cams[v].viewmatrix;
+            in.projmatrix = cams[v].projmatrix;
+            in.campos = cams[v].campos;
+            in.tan_fovx = cams[v].tan_fovx;
+            in.tan_fovy = cams[v].tan_fovy;
+        }
+        GeomView g = GeomView::carve(geometry_states[v], P);
+        char* base = (char*)ctx->geom.p + (size_t)v * per_view;
+        uint32_t* keys_in = (uint32_t*)(base);
+        uint32_t* keys_out = (uint32_t*)(base + arr);
+        uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
+        uint32_t* perm = (uint32_t*)(base + 3 * arr);
+        uint32_t* offsets = (uint32_t*)(base + 4 * arr);
+        void* cub_tmp = base + 5 * arr;
+        unsigned long long* total64 = (unsigned long long*)(base + 5 * arr + tmp);
+        {
+            StageTimer t(ctx, ST_PREPROCESS, s);
+            rc = launch_preprocess(in, g, radii_v[v], keys_in, s);
+            if (rc) return rc;
+            ctx->launches += 1;
+        }
+        {
+            StageTimer t(ctx, ST_DEPTH_SORT, s);
+            iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vals_in);
+            SGB_LAUNCH_CHECK("iota_kernel", in.debug, s);
+            SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_in, keys_out, vals_in, perm, P, 0, 32, s));
+            ctx->launches += 1;
+            ctx->lib_launches += 1;
+        }
+        {
+            StageTimer t(ctx, ST_SCAN, s);
+            ctx->lib_launches += 1;
+            ctx->launches += 1;
+            // keys_in is free after the sort: reuse it for the permuted counts
+            SGB_CUDA(cudaMemsetAsync(total64, 0, sizeof(unsigned long long), s));
+            gather_counts_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, perm, g.tiles_touched, keys_in, total64);
+            SGB_LAUNCH_CHECK("gather_counts_kernel", in.debug, s);
+            SGB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_tmp, keys_in, offsets, P, s));
+        }
+        SGB_CUDA(cudaMemcpyAsync(h + v, total64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        ctx->d_perm[v] = perm;
+        ctx->d_offsets[v] = offsets;
     }
-    {
-        StageTimer t(ctx, ST_DEPTH_SORT, s);
-        iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vals_in);
-        SGB_LAUNCH_CHECK("iota_kernel", in.debug, s);
-        SGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_tmp, keys_in, keys_out, vals_in, perm, P, 0, 32, s));
-        ctx->launches += 1;
-        ctx->lib_launches += 1;
-    }
-    {
-        StageTimer t(ctx, ST_SCAN, s);
-        ctx->lib_launches += 1;
-        ctx->launches += 1;
-        // keys_in is free after the sort: reuse it for the permuted counts
-        gather_counts_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, perm, g.tiles_touched, keys_in);
-        SGB_LAUNCH_CHECK("gather_counts_kernel", in.debug, s);
-        SGB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_tmp, keys_in, offsets, P, s));
-    }
-    uint32_t* h = (uint32_t*)ctx->pinned;
-    SGB_CUDA(cudaMemcpyAsync(h, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SGB_CUDA(cudaStreamSynchronize(s));
-    *R_host = (int64_t)h[0];
+    // 64-bit sums == last element of the 32-bit scans whenever they fit (the caller rejects anything above int32)
+    for (int v = 0; v < V; v++) R_host[v] = (int64_t)h[v];
     ctx->last_P = P;
-    ctx->d_perm = perm;
-    ctx->d_offsets = offsets;
+    ctx->last_V = V;
     return SGB_OK;
 }
 
 template <typename KeyT>
-static int run_binning_t(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                         const int32_t* radii, dim3 tile_grid, cudaStream_t s) {
+static int run_binning_t(sgb_ctx* ctx, const sgb_view_inputs& in, int view_slot, int64_t R, GeomView g, BinView b,
+                         ImgView im, const int32_t* radii, dim3 tile_grid, cudaStream_t s) {
     const uint32_t tiles = tile_grid.x * tile_grid.y;
     size_t sort_tmp = 0;
     const int bits = (int)higher_msb(tiles);
@@ -201,8 +229,9 @@ static int run_binning_t(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Geo
     void* cub_tmp = base + 2 * karr + varr;
     {
         StageTimer t(ctx, ST_EMIT, s);
-        emit_instances_kernel<KeyT><<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm, ctx->d_offsets, g.rec, radii,
-                                                                      tile_grid, keys_unsorted, vals_unsorted);
+        emit_instances_kernel<KeyT><<<(in.P + 255) / 256, 256, 0, s>>>(in.P, ctx->d_perm[view_slot],
+                                                                      ctx->d_offsets[view_slot], g.rec, radii, tile_grid,
+                                                                      keys_unsorted, vals_unsorted);
         SGB_LAUNCH_CHECK("emit_instances_kernel", in.debug, s);
         ctx->launches += 1;
     }
@@ -221,7 +250,26 @@ static int run_binning_t(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, Geo
     return SGB_OK;
 }
 
-int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+// Grows the tile-sort scratch to what R instances need (a batch reserves for its largest view up front so that
+// no cudaFree / cudaMalloc — an implicit device sync — lands between the views).
+int reserve_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, cudaStream_t s) {
+    if (R <= 0) return SGB_OK;
+    const size_t tiles = (size_t)((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    const int bits = (int)higher_msb((uint32_t)tiles);
+    size_t sort_tmp = 0;
+    size_t ksz = 4;
+    if (tiles <= 0xFFFFu) {
+        ksz = 2;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint16_t*)nullptr, (uint16_t*)nullptr, (uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, R, 0, bits, s);
+    } else {
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, R, 0, bits, s);
+    }
+    return ctx->bin.ensure(2 * align_up(ksz * (size_t)R) + align_up(sizeof(uint32_t) * (size_t)R) + align_up(sort_tmp));
+}
+
+int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int view_slot, int64_t R, GeomView g, BinView b, ImgView im,
                 const int32_t* radii, cudaStream_t s) {
     dim3 tile_grid((in.W + SGB_TILE - 1) / SGB_TILE, (in.H + SGB_TILE - 1) / SGB_TILE, 1);
     const size_t tiles = (size_t)tile_grid.x * tile_grid.y;
@@ -229,13 +277,13 @@ int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, 
         SGB_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), s));  // rasterizer_impl.cu:313
         return SGB_OK;
     }
-    if (ctx->last_P != in.P || !ctx->d_perm) {
+    if (ctx->last_P != in.P || view_slot < 0 || view_slot >= ctx->last_V || !ctx->d_perm[view_slot]) {
         set_error("sgb_forward_render called without a matching sgb_forward_geometry on this ctx");
         return SGB_E_INVALID;
     }
     // 16-bit tile keys halve the key traffic of the R-sized sort whenever the tile count allows it
-    if (tiles <= 0xFFFFu) return run_binning_t<uint16_t>(ctx, in, R, g, b, im, radii, tile_grid, s);
-    return run_binning_t<uint32_t>(ctx, in, R, g, b, im, radii, tile_grid, s);
+    if (tiles <= 0xFFFFu) return run_binning_t<uint16_t>(ctx, in, view_slot, R, g, b, im, radii, tile_grid, s);
+    return run_binning_t<uint32_t>(ctx, in, view_slot, R, g, b, im, radii, tile_grid, s);
 }
 
 }  // namespace sgb

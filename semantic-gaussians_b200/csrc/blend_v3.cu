@@ -245,6 +245,74 @@ __global__ void __launch_bounds__(kThreads) alpha_pass_kernel(
 }
 
 // ------------------------------------------------------------------------------------ forward
+// Non-finite features.  The GEMM-shaped kernels multiply every (pixel, entry) pair of a tile, zero weights
+// included, and 0 * inf = NaN: one non-finite feature row would poison every pixel of every tile its Gaussian is
+// binned to, where the reference only touches the pixels that actually blend it (forward.cu:340-356 `continue`s
+// before the accumulation).  A pair is blended exactly when its weight alpha * T is non-zero (alpha >= 1/255 and
+// T >= 1e-4 on that path), so the exact semantics are "accumulate only where w != 0".  Guarding every FMA would
+// double the inner loop; instead the epilogue tests the accumulators (acc * 0 summed: NaN iff any accumulator is
+// non-finite, 32 packed FMAs per lane) and only a warp that sees a non-finite value recomputes its 32 px x CH
+// slice with the guarded loop below, straight from the weight rows and feature rows in global memory.
+template <int MCH>
+__device__ __forceinline__ bool acc_nonfinite(const float2 (&acc)[8][MCH / 2]) {
+    float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH / 2; k++) z = ffma2(acc[i][k], make_float2(0.f, 0.f), z);
+    const float t = z.x + z.y;
+    return __any_sync(0xffffffffu, t != t);
+}
+
+// RING = true: lane cg owns channels {4cg..4cg+3} U {32+4cg..} of the slice (blend_forward_tma_kernel);
+// false: channels cg*MCH .. cg*MCH+MCH-1 (blend_forward_v3_kernel).  Self-contained (own accumulators, own
+// stores) so that the fast path's accumulators never have their address taken.
+template <int MCH, bool RING>
+__device__ __noinline__ void forward_redo_guarded(const PoolView& pool, uint32_t n, uint32_t dbase,
+                                                  const float* __restrict__ features, int C, int ch0, int nch,
+                                                  int warp, int woff, int cg, const float* __restrict__ bg_color,
+                                                  const float* __restrict__ final_T, int W, int H, uint32_t row,
+                                                  uint32_t col0, float* __restrict__ out_color) {
+    float acc[8][MCH];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < MCH; k++) acc[i][k] = 0.f;
+    for (uint32_t e = 0; e < n; e++) {
+        const WChunk* ck = pool.chunks + chunk_of(pool, dbase, (int)(e / kChunkEntries));
+        const int s = (int)(e & (kChunkEntries - 1));
+        const uint2 meta = ck->meta[s];
+        if (!((meta.y >> warp) & 1u)) continue;
+        const float* fr = features + (size_t)meta.x * C + ch0;
+        float f[MCH];
+#pragma unroll
+        for (int k = 0; k < MCH; k++) {
+            const int chl = RING ? ((k >> 2) * 32 + cg * 4 + (k & 3)) : (cg * MCH + k);
+            f[k] = chl < nch ? __ldg(fr + chl) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float w = ck->w[s][woff + i];
+            if (w != 0.f) {
+#pragma unroll
+                for (int k = 0; k < MCH; k++) acc[i][k] = fmaf(f[k], w, acc[i][k]);
+            }
+        }
+    }
+    if (row >= (uint32_t)H) return;
+    const size_t plane = (size_t)H * W;
+#pragma unroll
+    for (int k = 0; k < MCH; k++) {
+        const int chl = RING ? ((k >> 2) * 32 + cg * 4 + (k & 3)) : (cg * MCH + k);
+        if (chl >= nch) continue;
+        const float bgc = bg_color[ch0 + chl];
+        float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (col0 + i < (uint32_t)W) dst[i] = acc[i][k] + final_T[(size_t)W * row + col0 + i] * bgc;
+    }
+}
+
 template <int CH, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
     int W, int H, int C, const float* __restrict__ features, const float* __restrict__ bg_color,
@@ -304,10 +372,14 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_v3_kernel(
         }
         e += m;
     }
-
     // out = acc + T * bg (forward.cu:372-373)
     const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
     const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (acc_nonfinite<MCH>(acc)) {
+        forward_redo_guarded<MCH, false>(pool, n, dbase, features, C, ch0, nch, warp, woff, cg, bg_color, final_T, W, H,
+                                         row, col0, out_color);
+        return;
+    }
     if (row < (uint32_t)H) {
         const size_t plane = (size_t)H * W;
         const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
@@ -501,9 +573,13 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
-
     const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
     const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    if (acc_nonfinite<MCH>(acc)) {
+        forward_redo_guarded<MCH, true>(pool, n, dbase, features, C, ch0, nch, warp, woff, cg, bg_color, final_T, W, H,
+                                        row, col0, out_color);
+        return;
+    }
     if (row < (uint32_t)H) {
         const size_t plane = (size_t)H * W;
         const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
@@ -919,77 +995,76 @@ size_t pool_bytes(int tiles, uint32_t chunks, int64_t R, PoolView* v, void* base
 
 }  // namespace
 
-// Runs the alpha pass into the ctx pool, growing the pool and retrying when it was too small.
-// Synchronises the stream (4-byte read-back of the overflow flag).
-static int run_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                          float* out_depth, PoolView* pv, cudaStream_t s) {
-    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
-    // The pool still holds this view's weight rows when the backward directly follows its forward on
-    // the same ctx (the usual training step): same binning state, same sizes, nothing ran in between.
-    if (ctx->pool_valid && ctx->pool_key_bin == (const void*)b.point_list && ctx->pool_key_R == R &&
-        ctx->pool_key_W == in.W && ctx->pool_key_H == in.H && ctx->pool_key_P == in.P && !out_depth) {
-        pool_bytes(tiles, ctx->pool_key_chunks, R, pv, ctx->pool.p);
-        return SGB_OK;
+// ---- weight-pool slots ---------------------------------------------------------------------------------------
+static inline int num_tiles(const sgb_view_inputs& in) {
+    return ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+}
+
+static PoolSlot* pool_find(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, BinView b) {
+    for (PoolSlot& sl : ctx->pools)
+        if (sl.valid && sl.key_bin == (const void*)b.point_list && sl.key_R == R && sl.key_W == in.W && sl.key_H == in.H &&
+            sl.key_P == in.P) {
+            sl.stamp = ++ctx->pool_clock;
+            return &sl;
+        }
+    return nullptr;
+}
+
+// Slot for a view that is about to be (re)built: the one already keyed by this binning state (a new forward
+// through the same pointer replaces it), else an empty one, else the least recently used.
+static PoolSlot* pool_acquire(sgb_ctx* ctx, BinView b) {
+    PoolSlot* pick = nullptr;
+    for (PoolSlot& sl : ctx->pools)
+        if (sl.key_bin == (const void*)b.point_list) { pick = &sl; break; }
+    if (!pick)
+        for (PoolSlot& sl : ctx->pools)
+            if (!sl.valid && !sl.key_bin) { pick = &sl; break; }
+    if (!pick) {
+        pick = &ctx->pools[0];
+        for (PoolSlot& sl : ctx->pools)
+            if (sl.stamp < pick->stamp) pick = &sl;
     }
-    ctx->pool_valid = false;
-    // first guess: ~8 chunks (128 touching Gaussians) per tile, bounded by the instance count
+    pick->valid = false;
+    pick->key_bin = (const void*)b.point_list;
+    pick->stamp = ++ctx->pool_clock;
+    return pick;
+}
+
+static uint64_t pool_first_guess(sgb_ctx* ctx, int tiles, int64_t R) {
+    // ~8 chunks (128 touching Gaussians) per tile, bounded by the instance count, at least the high-water mark
     uint64_t guess = (uint64_t)tiles * 8;
     const uint64_t by_R = (uint64_t)(R / kChunkEntries) + (uint64_t)tiles;
     if (guess > by_R) guess = by_R;
     if (guess < ctx->pool_chunks_hint) guess = ctx->pool_chunks_hint;
     if (guess < 16) guess = 16;
+    return guess;
+}
+
+static int launch_alpha_pass(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g, BinView b, ImgView im,
+                             float* out_depth, const PoolView& pv, cudaStream_t s) {
+    const int tiles = num_tiles(in);
     const size_t smem = sizeof(AlphaSmem);
     static DeviceOnce attr_set;
     if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SGB_CUDA(cudaFuncSetAttribute(alpha_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    for (int attempt = 0; attempt < 4; attempt++) {
-        const uint32_t chunks = (uint32_t)guess;
-        int rc = ctx->pool.ensure(pool_bytes(tiles, chunks, R, nullptr, nullptr));
-        if (rc) return rc;
-        pool_bytes(tiles, chunks, R, pv, ctx->pool.p);
-        SGB_CUDA(cudaMemsetAsync(pv->hdr, 0, sizeof(PoolHdr), s));
-        {
-            StageTimer t(ctx, ST_ALPHA, s);
-            if (out_depth)
-                alpha_pass_kernel<true><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec, im.final_T,
-                                                                    im.n_contrib, im.tile_last, out_depth, *pv);
-            else
-                alpha_pass_kernel<false><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec,
-                                                                     im.final_T, im.n_contrib, im.tile_last, nullptr, *pv);
-            SGB_LAUNCH_CHECK("alpha_pass_kernel", in.debug, s);
-            ctx->launches += 1;
-        }
-        uint32_t* h = (uint32_t*)ctx->pinned + 4;
-        SGB_CUDA(cudaMemcpyAsync(h, pv->hdr, sizeof(PoolHdr), cudaMemcpyDeviceToHost, s));
-        SGB_CUDA(cudaStreamSynchronize(s));
-        const uint32_t used = h[0], overflow = h[1];
-        if (!overflow) {
-            ctx->stat_blended_pairs = (int64_t)(*reinterpret_cast<const unsigned long long*>(h + 2));
-            ctx->stat_pool_chunks = used;
-            if (used > ctx->pool_chunks_hint) ctx->pool_chunks_hint = used + used / 16 + 16;
-            ctx->pool_valid = true;
-            ctx->pool_key_bin = (const void*)b.point_list;
-            ctx->pool_key_R = R;
-            ctx->pool_key_W = in.W;
-            ctx->pool_key_H = in.H;
-            ctx->pool_key_P = in.P;
-            ctx->pool_key_chunks = chunks;
-            return SGB_OK;
-        }
-        guess = (uint64_t)used + used / 8 + 64;  // the counter kept counting: this is the real demand
-    }
-    set_error("weight pool kept overflowing");
-    return SGB_E_NOMEM;
+    SGB_CUDA(cudaMemsetAsync(pv.hdr, 0, sizeof(PoolHdr), s));
+    StageTimer t(ctx, ST_ALPHA, s);
+    if (out_depth)
+        alpha_pass_kernel<true><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec, im.final_T,
+                                                            im.n_contrib, im.tile_last, out_depth, pv);
+    else
+        alpha_pass_kernel<false><<<tiles, kThreads, smem, s>>>(im.ranges, b.point_list, in.W, in.H, g.rec, im.final_T,
+                                                             im.n_contrib, im.tile_last, nullptr, pv);
+    SGB_LAUNCH_CHECK("alpha_pass_kernel", in.debug, s);
+    ctx->launches += 1;
+    return SGB_OK;
 }
 
-int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                     const float* colors, float* out_color, cudaStream_t s) {
-    PoolView pv;
-    int rc = run_alpha_pass(ctx, in, R, g, b, im, nullptr, &pv, s);
-    if (rc) return rc;
-    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+static int launch_forward_gemm(sgb_ctx* ctx, const sgb_view_inputs& in, ImgView im, const float* colors,
+                               float* out_color, const PoolView& pv, cudaStream_t s) {
+    const int tiles = num_tiles(in);
     const int chunks = (in.C + 63) / 64;
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     StageTimer t(ctx, ST_BLEND_FWD, s);
@@ -1013,46 +1088,129 @@ int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomVie
     return SGB_OK;
 }
 
-int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                      const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
-                      float* dL_dopacity, float* dL_dcolors, cudaStream_t s) {
-    PoolView pv;
-    // the weight rows are scratch, not saved state: rebuild them (one chain pass, ~the cost of a 3-channel render)
-    int rc = run_alpha_pass(ctx, in, R, g, b, im, nullptr, &pv, s);
+// pinned readback layout: [0, 8 * kMaxBatch) the R values of a geometry batch; then one PoolHdr (16 B) per view slot
+static inline PoolHdr* pinned_hdr(sgb_ctx* ctx, int view_slot) {
+    return reinterpret_cast<PoolHdr*>(reinterpret_cast<char*>(ctx->pinned) + 8 * kMaxBatch) + view_slot;
+}
+
+// Alpha pass + forward GEMM of one view into a pool slot; no stream sync.  The forward GEMM is enqueued before the
+// pool-size check is read back (a too-small pool only yields garbage pixels — every chunk index is clamped into the
+// pool — and the view is redone): the GPU never idles between the two kernels.
+int blend_forward_v3_enqueue(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
+                             ImgView im, const float* colors, float* out_color, cudaStream_t s) {
+    const int tiles = num_tiles(in);
+    PoolSlot* sl = pool_acquire(ctx, b);
+    uint64_t want = pool_first_guess(ctx, tiles, R);
+    if (sl->chunks > want && sl->mem.cap >= pool_bytes(tiles, sl->chunks, R, nullptr, nullptr)) want = sl->chunks;
+    const uint32_t chunks = (uint32_t)want;
+    int rc = sl->mem.ensure(pool_bytes(tiles, chunks, R, nullptr, nullptr));
     if (rc) return rc;
-    const int tiles = ((in.W + SGB_TILE - 1) / SGB_TILE) * ((in.H + SGB_TILE - 1) / SGB_TILE);
+    sl->chunks = chunks;
+    PoolView pv;
+    pool_bytes(tiles, chunks, R, &pv, sl->mem.p);
+    rc = launch_alpha_pass(ctx, in, g, b, im, nullptr, pv, s);
+    if (rc) return rc;
+    rc = launch_forward_gemm(ctx, in, im, colors, out_color, pv, s);
+    if (rc) return rc;
+    SGB_CUDA(cudaMemcpyAsync(pinned_hdr(ctx, view_slot), pv.hdr, sizeof(PoolHdr), cudaMemcpyDeviceToHost, s));
+    return SGB_OK;
+}
+
+// After the stream sync: 0 = the view is done (slot validated), 1 = the pool overflowed — the slot was grown to the
+// real demand (the counter keeps counting past capacity) and the caller enqueues the view again; < 0 error.
+int blend_forward_v3_finish(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, BinView b) {
+    PoolSlot* sl = nullptr;
+    for (PoolSlot& c : ctx->pools)
+        if (c.key_bin == (const void*)b.point_list) { sl = &c; break; }
+    if (!sl) { set_error("weight-pool slot of the view vanished"); return SGB_E_INVALID; }
+    const PoolHdr h = *pinned_hdr(ctx, view_slot);
+    if (h.overflow) {
+        const uint64_t need = (uint64_t)h.counter + h.counter / 8 + 64;
+        if (need > ctx->pool_chunks_hint) ctx->pool_chunks_hint = need;
+        sl->chunks = 0;  // re-carve with the new hint
+        return 1;
+    }
+    ctx->stat_blended_pairs = (int64_t)h.blended;
+    ctx->stat_pool_chunks = h.counter;
+    if (h.counter > ctx->pool_chunks_hint) ctx->pool_chunks_hint = (uint64_t)h.counter + h.counter / 16 + 16;
+    sl->valid = true;
+    sl->key_R = R;
+    sl->key_W = in.W;
+    sl->key_H = in.H;
+    sl->key_P = in.P;
+    return 0;
+}
+
+// Weight rows of a view for its backward: the slot its forward filled, else rebuilt here (one more alpha pass and a
+// stream sync for the pool check — only when the forward ran through another ctx or the slot was recycled).
+static int pool_for_backward(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                             PoolView* pv, cudaStream_t s) {
+    const int tiles = num_tiles(in);
+    if (PoolSlot* hit = pool_find(ctx, in, R, b)) {
+        pool_bytes(tiles, hit->chunks, R, pv, hit->mem.p);
+        return SGB_OK;
+    }
+    for (int attempt = 0; attempt < 4; attempt++) {
+        PoolSlot* sl = pool_acquire(ctx, b);
+        const uint32_t chunks = (uint32_t)pool_first_guess(ctx, tiles, R);
+        int rc = sl->mem.ensure(pool_bytes(tiles, chunks, R, nullptr, nullptr));
+        if (rc) return rc;
+        sl->chunks = chunks;
+        pool_bytes(tiles, chunks, R, pv, sl->mem.p);
+        rc = launch_alpha_pass(ctx, in, g, b, im, nullptr, *pv, s);
+        if (rc) return rc;
+        SGB_CUDA(cudaMemcpyAsync(pinned_hdr(ctx, 0), pv->hdr, sizeof(PoolHdr), cudaMemcpyDeviceToHost, s));
+        SGB_CUDA(cudaStreamSynchronize(s));
+        rc = blend_forward_v3_finish(ctx, 0, in, R, b);
+        if (rc <= 0) return rc;
+    }
+    set_error("weight pool kept overflowing");
+    return SGB_E_NOMEM;
+}
+
+int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                               const float* dL_dpix, float* dL_dcolors, cudaStream_t s) {
+    PoolView pv;
+    int rc = pool_for_backward(ctx, in, R, g, b, im, &pv, s);
+    if (rc) return rc;
+    const int tiles = num_tiles(in);
     const int chunks = (in.C + 63) / 64;
+    const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
+    static DeviceOnce attr_set;
+    if (attr_set.first_use_on_device())
+        SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+    StageTimer t(ctx, ST_DFEATURE, s);
+    ctx->launches += 1;
+    dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
+    SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
+    return SGB_OK;
+}
+
+int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                            const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                            float* dL_dopacity, cudaStream_t s) {
+    PoolView pv;
+    int rc = pool_for_backward(ctx, in, R, g, b, im, &pv, s);
+    if (rc) return rc;
+    const int tiles = num_tiles(in);
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     const size_t smem_g = sizeof(float) * (8 * kSeg * 32 + 2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
-    const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
     static DeviceOnce attr_set;
     if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
     }
-    // dL/dfeature first: it needs only the weight rows and dL/dout, and it is the one large
-    // gradient, so a data-parallel caller can start reducing it while the chain runs (sgb200.h)
-    {
-        StageTimer t(ctx, ST_DFEATURE, s);
-        ctx->launches += 1;
-        dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
-        SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
-    }
-    if (ctx->feature_grad_event) SGB_CUDA(cudaEventRecord(ctx->feature_grad_event, s));
-    {
-        StageTimer t(ctx, ST_BLEND_BWD, s);
-        ctx->launches += 1;
-        if (vec)
-            chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                            im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
-                                                                            dL_dopacity);
-        else
-            chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                             im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
-                                                                             dL_dopacity);
-        SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
-    }
+    StageTimer t(ctx, ST_BLEND_BWD, s);
+    ctx->launches += 1;
+    if (vec)
+        chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                        im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
+                                                                        dL_dopacity);
+    else
+        chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
+                                                                         im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
+                                                                         dL_dopacity);
+    SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
     return SGB_OK;
 }
 

@@ -109,7 +109,7 @@ enum Stage {
     ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_TRANSPOSE, ST_FUSION_GATHER, ST_ALPHA, ST_DFEATURE,
     ST_COUNT
 };
-constexpr int kProfRing = 128;
+constexpr int kProfRing = 320;
 struct Profiler {
     bool on = false;
     cudaEvent_t ev[ST_COUNT][kProfRing][2];
@@ -118,30 +118,44 @@ struct Profiler {
 };
 }  // namespace sgb
 
+namespace sgb {
+constexpr int kMaxBatch = 8;  // views per batched call == weight-pool slots kept per ctx
+
+// One weight pool (blend_v3.cu) = the per-tile alpha*T rows of ONE view.  A ctx keeps up to kMaxBatch of them so
+// that the backward of each view of a batch (or of a forward-forward-...-backward-backward sequence) finds the
+// rows its forward built.  A slot is identified by the view's binning-state pointer: a new forward through the
+// same pointer necessarily overwrites that slot, so a slot can never describe a different view's instance list.
+struct PoolSlot {
+    Scratch mem;
+    bool valid = false;
+    const void* key_bin = nullptr;
+    int64_t key_R = 0;
+    int key_W = 0, key_H = 0, key_P = 0;
+    uint32_t chunks = 0;   // capacity the slot was carved with
+    uint64_t stamp = 0;    // LRU clock
+};
+}  // namespace sgb
+
 struct sgb_ctx {
     int device = 0;
     sgb::Profiler prof;
     uint64_t launches = 0;       // kernels of this library launched through this ctx
     uint64_t lib_launches = 0;   // CUB device-wide calls (each several kernels)
-    sgb::Scratch geom;     // depth-sort keys/values, offsets, CUB temp
+    sgb::Scratch geom;     // depth-sort keys/values, offsets, CUB temp (one slice per view of a batch)
     sgb::Scratch bin;      // unsorted / sorted tile keys, unsorted values, CUB temp
-    sgb::Scratch misc;     // fusion: transposed feature map, z-buffer
-    sgb::Scratch pool;     // per-tile weight rows of the C-channel blend (blend_v3.cu)
+    sgb::Scratch misc;     // fusion: pixel-sorted visible list, z-buffer
+    sgb::PoolSlot pools[sgb::kMaxBatch];  // per-tile weight rows of the C-channel blend (blend_v3.cu)
+    uint64_t pool_clock = 0;
     uint64_t pool_chunks_hint = 0;  // high-water mark of the pool demand (chunks)
-    // identity of the view whose weight rows the pool currently holds (forward -> backward reuse)
-    bool pool_valid = false;
-    const void* pool_key_bin = nullptr;
-    int64_t pool_key_R = 0;
-    int pool_key_W = 0, pool_key_H = 0, pool_key_P = 0;
-    uint32_t pool_key_chunks = 0;
-    int64_t* pinned = nullptr;  // host-pinned readback slot(s)
+    int64_t* pinned = nullptr;  // host-pinned readback slots (1 KB)
     int64_t stat_blended_pairs = 0;  // last alpha pass: blended (pixel, Gaussian) pairs
     int64_t stat_pool_chunks = 0;    // last alpha pass: 16-entry weight-row chunks in use
     cudaEvent_t feature_grad_event = nullptr;  // caller-owned; recorded when dL_dcolors is final (sgb200.h)
-    // cached layout of the last sgb_forward_geometry call (consumed by sgb_forward_render)
+    // cached layout of the last sgb_forward_geometry[_batch] call (consumed by sgb_forward_render[_batch])
     int64_t last_P = 0;
-    uint32_t* d_perm = nullptr;     // [P] Gaussian ids in (depth bits, id) order
-    uint32_t* d_offsets = nullptr;  // [P] inclusive scan of tiles_touched in that order
+    int last_V = 0;
+    uint32_t* d_perm[sgb::kMaxBatch] = {};     // [P] Gaussian ids in (depth bits, id) order, per view of the batch
+    uint32_t* d_offsets[sgb::kMaxBatch] = {};  // [P] inclusive scan of tiles_touched in that order
 };
 
 namespace sgb {
@@ -178,20 +192,31 @@ struct DeviceOnce {
 int launch_preprocess(const sgb_view_inputs& in, GeomView g, int32_t* radii, uint32_t* depth_keys,
                       cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
-int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g, int32_t* radii,
-                             int64_t* R_host, cudaStream_t s);
-int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+// Depth order + scan of V views of the same Gaussians (cams[v] replaces the camera fields of `in`; V = 1 with
+// cams = nullptr is the single-view call): everything is enqueued back to back, ONE stream sync reads all R.
+int run_depth_order_and_scan(sgb_ctx* ctx, const sgb_view_inputs& in, int V, const sgb_camera* cams,
+                             void* const* geometry_states, int32_t* const* radii, int64_t* R_host, cudaStream_t s);
+int reserve_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, cudaStream_t s);
+int run_binning(sgb_ctx* ctx, const sgb_view_inputs& in, int view_slot, int64_t R, GeomView g, BinView b, ImgView im,
                 const int32_t* radii, cudaStream_t s);
 int launch_blend_forward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                          float* out_color, float* out_depth, cudaStream_t s);
 int launch_blend_backward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                           const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, cudaStream_t s);
-int blend_forward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                     const float* colors, float* out_color, cudaStream_t s);
-int blend_backward_v3(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
-                      const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
-                      float* dL_dopacity, float* dL_dcolors, cudaStream_t s);
+// C > 4 blend of one view, split so that a batch can enqueue all its views before the one stream sync:
+//   enqueue  alpha pass + forward GEMM into a weight-pool slot (no sync; pool header -> pinned slot `view_slot`)
+//   finish   after the stream was synchronised: 0 = done, 1 = the pool overflowed (slot grown: enqueue again)
+int blend_forward_v3_enqueue(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
+                             ImgView im, const float* colors, float* out_color, cudaStream_t s);
+int blend_forward_v3_finish(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, BinView b);
+// backward of one view in two halves (a batch runs all dL/dfeature kernels first, records the feature-gradient
+// event, then the chain kernels): `prepare` finds or rebuilds the view's weight rows.
+int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                               const float* dL_dpix, float* dL_dcolors, cudaStream_t s);
+int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
+                            const float* colors, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                            float* dL_dopacity, cudaStream_t s);
 int launch_geom_backward(const sgb_view_inputs& in, GeomView g, const int32_t* radii, const float* cov3D,
                          const float* dL_dcolor_rgb, const sgb_view_grads& gr, cudaStream_t s);
 

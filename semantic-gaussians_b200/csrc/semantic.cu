@@ -356,16 +356,34 @@ __global__ void label_argmax_kernel(int K, int first_class, long long N, const f
 // formulation — index_select of the (C,K) table + dot — moves 1.5x the bytes in three kernels).  Thread = 4
 // consecutive pixels, the pre-scaled table sits transposed [C][K+1] in shared memory (odd pitch: lanes with
 // different labels hit different banks, equal labels broadcast).
+// Pixels whose label lies outside [0, K) are IGNORED (ScanNet-style -1 / 255 "unannotated"): zero gradient, no loss
+// term, and they do not count in the normaliser.  The number of valid pixels is counted first (loss[1]).
+template <typename LabelT>
+__global__ void __launch_bounds__(256) count_valid_labels_kernel(int K, long long N, const LabelT* __restrict__ labels,
+                                                                 double* __restrict__ valid) {
+    long long n = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+        const long long l = (long long)labels[p];
+        n += (l >= 0 && l < K);
+    }
+    int ni = (int)n;
+    ni = __reduce_add_sync(0xffffffffu, ni);
+    if ((threadIdx.x & 31) == 0 && ni) atomicAdd(valid, (double)ni);
+}
+
 template <bool VEC, typename LabelT>
 __global__ void __launch_bounds__(256) distill_loss_kernel(int C, int K, long long N, const float* __restrict__ render,
                                                            const float* __restrict__ emb, const LabelT* __restrict__ labels,
-                                                           float scale, float* __restrict__ dL, double* __restrict__ loss) {
-    extern __shared__ float Es[];  // [C][Kp]
-    const int Kp = K | 1;
+                                                           float* __restrict__ dL, double* __restrict__ loss) {
+    extern __shared__ float Es[];  // [C][Kp]; column K is all zero: the "ignored" class
+    const int Kp = (K + 1) | 1;
+    const double nvalid = loss[1];
+    const float scale = (float)(-1.0 / ((double)C * (nvalid > 0.0 ? nvalid : 1.0)));
     for (int e = threadIdx.x; e < C * K; e += blockDim.x) {
         const int k = e / C, c = e - k * C;  // coalesced read of emb (K,C)
         Es[c * Kp + k] = __ldg(emb + e) * scale;
     }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) Es[c * Kp + K] = 0.f;
     __syncthreads();
     const long long p0 = VEC ? ((long long)blockIdx.x * 256 + threadIdx.x) * 4 : (long long)blockIdx.x * 1024 + threadIdx.x;
     long long px[4];
@@ -373,8 +391,8 @@ __global__ void __launch_bounds__(256) distill_loss_kernel(int C, int K, long lo
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         px[i] = VEC ? p0 + i : p0 + (long long)i * 256;
-        long long l = px[i] < N ? (long long)labels[px[i]] : 0;
-        lab[i] = (int)min(max(l, 0ll), (long long)K - 1);  // out-of-range labels are clamped, never read out of bounds
+        const long long l = px[i] < N ? (long long)labels[px[i]] : -1;
+        lab[i] = (l >= 0 && l < K) ? (int)l : K;  // out-of-range labels read the zero column: ignored
     }
     float acc = 0.f;
     if (px[0] < N) {
@@ -516,12 +534,15 @@ int sgb_distill_loss(int32_t C, int32_t K, int64_t N, const float* render, const
     cudaStream_t s = (cudaStream_t)stream;
     if (C <= 0 || K <= 0 || N < 0) { set_error("sgb_distill_loss: need C > 0, K > 0, N >= 0"); return SGB_E_INVALID; }
     if (!loss) { set_error("sgb_distill_loss: null loss"); return SGB_E_INVALID; }
-    SGB_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), s));
+    SGB_CUDA(cudaMemsetAsync(loss, 0, 2 * sizeof(double), s));
     if (N == 0) return SGB_OK;
     if (!render || !class_emb || !labels || !dL_drender) { set_error("sgb_distill_loss: null argument"); return SGB_E_INVALID; }
-    const size_t smem = sizeof(float) * (size_t)C * (K | 1);
+    const size_t smem = sizeof(float) * (size_t)C * ((K + 1) | 1);
     if (smem > 200 * 1024) { set_error("sgb_distill_loss: C x K = %d x %d does not fit shared memory", C, K); return SGB_E_INVALID; }
-    const float scale = (float)(-1.0 / ((double)C * (double)N));
+    if (labels_are_int64)
+        count_valid_labels_kernel<long long><<<148 * 4, 256, 0, s>>>(K, (long long)N, (const long long*)labels, loss + 1);
+    else
+        count_valid_labels_kernel<int><<<148 * 4, 256, 0, s>>>(K, (long long)N, (const int*)labels, loss + 1);
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(render) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(dL_drender) & 15) == 0);
     const unsigned blocks = (unsigned)((N + 1023) / 1024);
@@ -532,7 +553,7 @@ int sgb_distill_loss(int32_t C, int32_t K, int64_t N, const float* render, const
             SGB_CUDA(cudaFuncSetAttribute(distill_loss_kernel<VECF, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           200 * 1024));                                                               \
         distill_loss_kernel<VECF, T><<<blocks, 256, smem, s>>>(C, K, (long long)N, render, class_emb, (const T*)labels, \
-                                                               scale, dL_drender, loss);                              \
+                                                               dL_drender, loss);                                     \
     } while (0)
     if (vec && labels_are_int64) SGB_DISTILL(true, long long);
     else if (vec) SGB_DISTILL(true, int);

@@ -86,25 +86,44 @@ class OverlappedFeatureGradReduce:
     only touch small tensors.  `start(grad)` — called right after `.backward()` returned on the host,
     while the GPU is still working through those kernels — makes a communication stream wait on that
     event only and launches the NCCL sum there; `finish()` joins it back into the current stream.
-    One view per rank per exchange (autograd adds a second view's gradient after the event).
+
+    The native event marks the moment the RAW gradient buffer is final.  That buffer is the leaf's ``.grad`` only
+    when the leaf had no gradient before the backward (autograd then adopts the buffer); otherwise AccumulateGrad
+    enqueues an in-place add AFTER the event and the early all-reduce would race with it.  `arm(param)` — called
+    before `.backward()` — records which case applies; with a pre-existing ``.grad`` (a second local view,
+    ``zero_grad(set_to_none=False)``) or without `arm`, `start` orders the exchange after everything enqueued on
+    the current stream (correct, no overlap).
     Create the process group with ``nccl_overlap_options()`` or the overlap will not materialise."""
 
     def __init__(self, device: torch.device, group=None):
         from . import _lib
         self.device, self.group = torch.device(device), group
-        self.comm_stream = torch.cuda.Stream(self.device, priority=-1)
-        self.event = torch.cuda.Event()
-        cur = torch.cuda.current_stream(self.device)
-        self.event.record(cur)                      # materialises the cudaEvent_t
-        self._ctx = _lib.ctx_for(self.device.index, cur.cuda_stream)
-        _lib.set_feature_grad_event(self._ctx, self.event.cuda_event)
+        with torch.cuda.device(self.device):
+            self.comm_stream = torch.cuda.Stream(self.device, priority=-1)
+            self.event = torch.cuda.Event()
+            cur = torch.cuda.current_stream(self.device)
+            self.event.record(cur)                      # materialises the cudaEvent_t
+            self._ctx = _lib.ctx_for(self.device.index, cur.cuda_stream)
+            _lib.set_feature_grad_event(self._ctx, self.event.cuda_event)
         self._work = None
+        self._fresh = None          # None: unknown (arm() not called) -> conservative ordering
 
-    def start(self, feature_grad: torch.Tensor) -> None:
+    def arm(self, param: torch.Tensor) -> None:
+        """Call before ``.backward()``: remembers whether the leaf's gradient buffer will be adopted as is."""
+        self._fresh = param.grad is None
+
+    def start(self, feature_grad: torch.Tensor, fresh: Optional[bool] = None) -> None:
         if not feature_grad.is_contiguous():
             raise ValueError("feature gradient must be contiguous (reduced in place)")
+        if fresh is None:
+            fresh = bool(self._fresh)
+        self._fresh = None
+        cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(self.event)
+            if fresh:
+                self.comm_stream.wait_event(self.event)     # final right after the dL/dfeature kernel
+            else:
+                self.comm_stream.wait_stream(cur)           # an accumulate kernel follows the event: wait for it
             self._work = dist.all_reduce(feature_grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self) -> None:

@@ -44,7 +44,9 @@ class GaussianModel(DensifyMixin):
     opacities, unnormalised quaternions, SH as (P,1,3) dc + (P,15,3) rest."""
 
     def __init__(self, sh_degree: int = 3):
-        self.active_sh_degree = sh_degree
+        # model/gaussian_model.py:47: a fresh model starts at degree 0; train.py:118 raises it with
+        # oneupSHdegree() every 1000 iterations (load_ply / load_dynamic_npz / from_activated set the full degree)
+        self.active_sh_degree = 0
         self.max_sh_degree = sh_degree
         self._xyz = torch.empty(0)
         self._features_dc = torch.empty(0)
@@ -60,6 +62,7 @@ class GaussianModel(DensifyMixin):
         """Build from activated values (numpy or torch): scales > 0, opacity in (0,1), unit quats."""
         t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device).contiguous()
         m = cls(sh_degree)
+        m.active_sh_degree = sh_degree      # an already-fitted scene (inference / bench): all bands active
         m._xyz = t(xyz)
         m._scaling = torch.log(t(scales))
         m._rotation = t(rotations)

@@ -27,6 +27,7 @@ def _check(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def _stream_ctx(t: torch.Tensor):
+    # callers hold `with torch.cuda.device(t.device)`: the kernels launch on a stream of t's device
     stream = torch.cuda.current_stream(t.device).cuda_stream
     return stream, _lib.ctx_for(t.device.index, stream)
 
@@ -50,11 +51,12 @@ def semantic_head(rendering: torch.Tensor, text_features: torch.Tensor, first_cl
         raise ValueError("first_class out of range")
     sim = torch.empty((K, H, W), dtype=torch.float32, device=r.device) if return_sim else None
     label = torch.empty((H, W), dtype=torch.int64, device=r.device) if return_label else None
-    stream, ctx = _stream_ctx(r)
-    _lib.check(_lib.load().sgb_semantic_head(ctx, C_, K, H * W, r.data_ptr(), t.data_ptr(), first_class,
-                                            sim.data_ptr() if sim is not None else None,
-                                            label.data_ptr() if label is not None else None, stream),
-               "sgb_semantic_head")
+    with torch.cuda.device(r.device):
+        stream, ctx = _stream_ctx(r)
+        _lib.check(_lib.load().sgb_semantic_head(ctx, C_, K, H * W, r.data_ptr(), t.data_ptr(), first_class,
+                                                sim.data_ptr() if sim is not None else None,
+                                                label.data_ptr() if label is not None else None, stream),
+                   "sgb_semantic_head")
     return sim, label
 
 
@@ -69,9 +71,10 @@ def feature_logits(features: torch.Tensor, text_features: torch.Tensor, pad_to: 
     K = t.shape[0]
     Kpad = ((K + pad_to - 1) // pad_to) * pad_to
     out = torch.empty((P, Kpad), dtype=torch.float32, device=f.device)
-    stream, _ = _stream_ctx(f)
-    _lib.check(_lib.load().sgb_feature_logits(P, C_, K, Kpad, f.data_ptr(), t.data_ptr(), out.data_ptr(), stream),
-               "sgb_feature_logits")
+    with torch.cuda.device(f.device):
+        stream, _ = _stream_ctx(f)
+        _lib.check(_lib.load().sgb_feature_logits(P, C_, K, Kpad, f.data_ptr(), t.data_ptr(), out.data_ptr(), stream),
+                   "sgb_feature_logits")
     return out
 
 
@@ -86,9 +89,10 @@ def label_argmax(planes: torch.Tensor, num_classes: Optional[int] = None, first_
         raise ValueError("bad num_classes / first_class")
     H, W = p.shape[1:]
     label = torch.empty((H, W), dtype=torch.int64, device=p.device)
-    stream, _ = _stream_ctx(p)
-    _lib.check(_lib.load().sgb_label_argmax(K, first_class, H * W, p.data_ptr(), label.data_ptr(), stream),
-               "sgb_label_argmax")
+    with torch.cuda.device(p.device):
+        stream, _ = _stream_ctx(p)
+        _lib.check(_lib.load().sgb_label_argmax(K, first_class, H * W, p.data_ptr(), label.data_ptr(), stream),
+                   "sgb_label_argmax")
     return label
 
 
@@ -100,6 +104,9 @@ def distill_loss_and_grad(rendering: torch.Tensor, class_emb: torch.Tensor, labe
         loss = -(rendering * class_emb[labels].permute(2, 0, 1)).mean()          # labels (H,W) int32/int64
         grad = d loss / d rendering                                               # (C,H,W)
 
+    Pixels whose label is outside [0, K) (ScanNet-style -1 / 255) are ignored: zero gradient, no loss term, and the
+    mean runs over the valid pixels only.
+
     Returns (loss: 0-d float64 CUDA tensor, grad: (C,H,W) float32).  Use as ``rendering.backward(grad)``."""
     r = _check(rendering.detach(), "rendering")
     e = _check(class_emb, "class_emb").to(r.device)
@@ -109,12 +116,13 @@ def distill_loss_and_grad(rendering: torch.Tensor, class_emb: torch.Tensor, labe
         raise ValueError("labels must be a CUDA int32/int64 tensor with H*W entries")
     lab = labels.contiguous()
     grad = torch.empty_like(r)
-    loss = torch.zeros((), dtype=torch.float64, device=r.device)
-    stream, _ = _stream_ctx(r)
-    _lib.check(_lib.load().sgb_distill_loss(r.shape[0], e.shape[0], r.shape[1] * r.shape[2], r.data_ptr(), e.data_ptr(),
-                                           lab.data_ptr(), int(lab.dtype == torch.int64), grad.data_ptr(),
-                                           loss.data_ptr(), stream), "sgb_distill_loss")
-    return loss, grad
+    loss2 = torch.zeros(2, dtype=torch.float64, device=r.device)      # [loss, number of non-ignored pixels]
+    with torch.cuda.device(r.device):
+        stream, _ = _stream_ctx(r)
+        _lib.check(_lib.load().sgb_distill_loss(r.shape[0], e.shape[0], r.shape[1] * r.shape[2], r.data_ptr(),
+                                               e.data_ptr(), lab.data_ptr(), int(lab.dtype == torch.int64),
+                                               grad.data_ptr(), loss2.data_ptr(), stream), "sgb_distill_loss")
+    return loss2[0], grad
 
 
 def render_semantic_labels(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, text_features: torch.Tensor,

@@ -142,3 +142,21 @@ def test_screen_size_and_opacity_pruning_and_reset():
     for _ in range(5):
         m.oneupSHdegree()
     assert m.active_sh_degree == 3
+
+
+def test_sh_degree_schedule_starts_at_zero_like_the_reference():
+    """model/gaussian_model.py:47 + train.py:118: a fresh model starts at SH degree 0 and oneupSHdegree() raises it
+    (capped at max_sh_degree); constructors of already-fitted scenes activate every band."""
+    import numpy as np
+    from semantic_gaussians_b200.gaussian_model import GaussianModel
+    m = GaussianModel(3)
+    assert m.active_sh_degree == 0 and m.max_sh_degree == 3
+    seen = []
+    for _ in range(5):
+        m.oneupSHdegree()
+        seen.append(m.active_sh_degree)
+    assert seen == [1, 2, 3, 3, 3]
+    rng = np.random.default_rng(0)
+    fitted = GaussianModel.from_activated(rng.standard_normal((4, 3)), np.full((4, 3), 0.1), np.tile([1.0, 0, 0, 0], (4, 1)),
+                                          np.full(4, 0.5), device="cpu")
+    assert fitted.active_sh_degree == 3
