@@ -41,6 +41,12 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C restatement (overrides an inherited OMP_NUM_THREADS)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def preprocess(means3D, scales, rotations, opacities, viewmatrix, projmatrix, campos, W, H, tanfovx, tanfovy,
                shs=None, colors_precomp=None, cov3D_precomp=None, scale_modifier=1.0, sh_degree=3):
     """forward.cu:155-256.  Returns a dict of per-Gaussian arrays."""

@@ -147,7 +147,7 @@ int sgb_profile_num_stages(void) { return ST_COUNT; }
 const char* sgb_profile_stage_name(int st) {
     static const char* names[ST_COUNT] = {"preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges",
                                           "blend_fwd", "blend_bwd", "geom_bwd", "fusion_project",
-                                          "fusion_transpose", "fusion_gather", "alpha_pass", "dfeature"};
+                                          "fusion_sort", "fusion_gather", "alpha_pass", "dfeature"};
     return (st >= 0 && st < ST_COUNT) ? names[st] : "";
 }
 uint64_t sgb_ctx_launch_count(const sgb_ctx* c, int library_calls) {
@@ -215,51 +215,56 @@ static int forward_render_impl(sgb_ctx* ctx, const sgb_view_inputs& in_common, i
     for (int v = 0; v < V; v++) maxR = num_rendered[v] > maxR ? num_rendered[v] : maxR;
     int rc = reserve_binning(ctx, in_common, in_common.P > 0 ? maxR : 0, s);
     if (rc) return rc;
-    bool pending[SGB_MAX_BATCH] = {};
-    auto enqueue_view = [&](int v, bool binning) -> int {
-        const sgb_view_inputs in = with_camera(in_common, cams, v);
-        const int64_t R = in.P > 0 ? num_rendered[v] : 0;
-        GeomView g = GeomView::carve(geometry_states[v], in.P > 0 ? in.P : 1);
-        BinView b = BinView::carve(binning_states[v], R);
-        ImgView im = ImgView::carve(image_states[v], in.W, in.H);
-        if (binning) {
-            int r = run_binning(ctx, in, v, R, g, b, im, radii[v], s);
-            if (r) return r;
-        }
-        const float* colors = in.colors_precomp ? in.colors_precomp : g.rgb;  // rasterizer_impl.cu:324
-        if (in.C > 4) {
-            pending[v] = true;
-            return blend_forward_v3_enqueue(ctx, v, in, R, g, b, im, colors, out_colors[v], s);
-        }
-        StageTimer t(ctx, ST_BLEND_FWD, s);
-        ctx->launches += 1;
-        return launch_blend_forward(in, g, b, im, colors, out_colors[v], out_depths ? out_depths[v] : nullptr, s);
-    };
+    struct View { sgb_view_inputs in; int64_t R; GeomView g; BinView b; ImgView im; const float* colors; };
+    View vw[SGB_MAX_BATCH];
+    const bool wide = in_common.C > 4;
     for (int v = 0; v < V; v++) {
-        rc = enqueue_view(v, true);
+        View& w = vw[v];
+        w.in = with_camera(in_common, cams, v);
+        w.R = w.in.P > 0 ? num_rendered[v] : 0;
+        w.g = GeomView::carve(geometry_states[v], w.in.P > 0 ? w.in.P : 1);
+        w.b = BinView::carve(binning_states[v], w.R);
+        w.im = ImgView::carve(image_states[v], w.in.W, w.in.H);
+        w.colors = w.in.colors_precomp ? w.in.colors_precomp : w.g.rgb;  // rasterizer_impl.cu:324
+        rc = run_binning(ctx, w.in, v, w.R, w.g, w.b, w.im, radii[v], s);
         if (rc) return rc;
+        if (wide) {
+            rc = blend_forward_v3_alpha(ctx, v, w.in, w.R, w.g, w.b, w.im, s);
+            if (rc) return rc;
+        } else {
+            StageTimer t(ctx, ST_BLEND_FWD, s);
+            ctx->launches += 1;
+            rc = launch_blend_forward(w.in, w.g, w.b, w.im, w.colors, out_colors[v], out_depths ? out_depths[v] : nullptr, s);
+            if (rc) return rc;
+        }
     }
-    if (in_common.C <= 4) return SGB_OK;
-    // one sync for the weight-pool checks of all views; an overflowed view (first view of a new scene) is redone
-    for (int attempt = 0; attempt < 4; attempt++) {
+    if (!wide) return SGB_OK;
+    // ONE sync validates the weight pools of all views (the host waits for the alpha passes only); a view whose
+    // pool overflowed (first view of a new scene) repeats its alpha pass.  Then the forward GEMMs are enqueued.
+    bool pending[SGB_MAX_BATCH];
+    for (int v = 0; v < V; v++) pending[v] = true;
+    for (int attempt = 0;; attempt++) {
         SGB_CUDA(cudaStreamSynchronize(s));
         bool again = false;
         for (int v = 0; v < V; v++) {
             if (!pending[v]) continue;
-            const sgb_view_inputs in = with_camera(in_common, cams, v);
-            const int64_t R = in.P > 0 ? num_rendered[v] : 0;
-            BinView b = BinView::carve(binning_states[v], R);
-            const int f = blend_forward_v3_finish(ctx, v, in, R, b);
+            View& w = vw[v];
+            const int f = blend_forward_v3_finish(ctx, v, w.in, w.R, w.b);
             if (f < 0) return f;
             if (f == 0) { pending[v] = false; continue; }
-            rc = enqueue_view(v, false);
+            if (attempt >= 3) { set_error("weight pool kept overflowing"); return SGB_E_NOMEM; }
+            rc = blend_forward_v3_alpha(ctx, v, w.in, w.R, w.g, w.b, w.im, s);
             if (rc) return rc;
             again = true;
         }
-        if (!again) return SGB_OK;
+        if (!again) break;
     }
-    set_error("weight pool kept overflowing");
-    return SGB_E_NOMEM;
+    for (int v = 0; v < V; v++) {
+        View& w = vw[v];
+        rc = blend_forward_v3_gemm(ctx, w.in, w.R, w.b, w.im, w.colors, out_colors[v], s);
+        if (rc) return rc;
+    }
+    return SGB_OK;
 }
 
 static int backward_impl(sgb_ctx* ctx, const sgb_view_inputs& in_common, int V, const sgb_camera* cams,

@@ -27,45 +27,13 @@
 // adds its Gaussians in depth order.
 #include <cstdlib>
 #include "common.cuh"
+#include "blend_pool.cuh"
 
 namespace sgb {
 
 namespace {
 
 constexpr int kThreads = SGB_TILE_PIX;
-constexpr int kChunkEntries = 16;
-constexpr uint32_t kNone = 0xFFFFFFFFu;
-
-struct __align__(16) WChunk {
-    uint32_t pad[4];
-    uint2 meta[kChunkEntries];             // x: Gaussian id, y: bit w = strip (warp) w has a non-zero weight
-    float w[kChunkEntries][SGB_TILE_PIX];  // alpha * T per pixel (tile-local index ty*16+tx)
-};
-static_assert(sizeof(WChunk) % 16 == 0, "WChunk must keep 16-byte alignment in an array");
-
-struct PoolHdr {
-    uint32_t counter;   // chunks handed out (keeps counting past capacity: the true demand)
-    uint32_t overflow;  // set when counter ran past capacity (results invalid, caller retries)
-    unsigned long long blended;  // (pixel, Gaussian) pairs that were blended: n-bar * W * H (reported by bench.py)
-};
-
-// A tile's chunks are found through a DIRECTORY (no linked list, no pointer chasing): chunk k of tile t is
-// dir[dirbase[t] + k] with dirbase[t] = ranges[t].x / 16 + t.  The tile ranges are disjoint intervals of the
-// sorted instance list, a tile with `len` instances needs at most ceil(len / 16) chunks, and
-// floor(x/16) + ceil(len/16) <= floor((x+len)/16) + 1, so the regions cannot overlap and R/16 + tiles + 1
-// directory slots always suffice — no scan, no capacity guess.
-struct PoolView {
-    PoolHdr* hdr;
-    uint32_t* dirbase;  // [tiles] first directory slot of the tile
-    uint32_t* count;    // [tiles] entries
-    uint32_t* dir;      // [R/16 + tiles + 1] chunk indices
-    WChunk* chunks;
-    uint32_t capacity;
-};
-
-__device__ __forceinline__ uint32_t chunk_of(const PoolView& pool, uint32_t dbase, int k) {
-    return min(__ldg(pool.dir + dbase + k), pool.capacity - 1);
-}
 
 template <int N>
 __device__ __forceinline__ void xreduce_step(float (&v)[8], int lane, int step) {
@@ -976,6 +944,285 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------ warp-autonomous chain backward
+// Second generation of the chain backward (round 2).  ncu on the CTA-synchronous kernel above (K3): FMA pipe 50 %,
+// issue 49 %, 16 warps/SM; executed FMAs = 2.0 x the algorithmic ones — every warp multiplied all 64 slots of every
+// segment of the TILE list although its 32-pixel strip is touched by ~85 % of the tile's entries, and segments of 64
+// padded the list by another ~22 %; one CTA-wide barrier per 16-channel slab.  Here every warp owns its strip end to
+// end and nothing is CTA-synchronous after the prologue:
+//   * the warp walks the tile list from the back and COMPACTS it on the fly to the entries whose strip-mask bit is
+//     set (ballot + popc ranks), 32 entries per segment: no zero-strip work, padding
+//     <= 31 slots per strip instead of <= 63 per tile;
+//   * s-pass per segment: S[32 px][32 entries] over all channels, lane tile 8 px x 4 entries (16 packed FMAs per 3
+//     LDS.128); the warp stages its own operands — the dL/dout slab [16 ch][32 px] by cp.async, the feature slab by
+//     4 x LDG.128 per lane (lane = entry) one slab ahead in registers, stored transposed [ch][entry];
+//   * S is parked in the warp's dL slab region (XOR-swizzled 16-byte chunks: conflict-free both ways) and lane = pixel
+//     runs the reference's back-to-front chain (backward.cu:477-550, dot-product form) over the 32 entries.
+// Shared memory 10.4 KB per warp, 2 CTAs/SM; the warps of a tile share their feature rows through L1/L2 only.
+struct __align__(16) ChainWarpSmem {
+    float DS[2][16][32];   // dL/dout slabs [buf][ch][px of the strip]; S[32 entries][32 px] aliases it after the s-pass
+    float FT[2][16][36];   // feature slabs [buf][ch][entry]
+    float4 RecA[32], RecB[32];
+    const float* Wrow[32];
+    uint32_t Gid[32];
+};
+constexpr int kMetaCap = 512;  // tile-list entries whose (id, mask) records are cached in shared memory
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
+    int W, int H, int C, const float* __restrict__ bg_color, const SplatRec* __restrict__ rec,
+    const float* __restrict__ features, const float* __restrict__ final_Ts, const float* __restrict__ dL_dpixels,
+    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity) {
+    constexpr int CK = 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint2 MetaS[kMetaCap];
+    __shared__ uint32_t Cdir[kMetaCap / kChunkEntries];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, eg = lane & 7;
+    ChainWarpSmem& ws = reinterpret_cast<ChainWarpSmem*>(smem_raw)[warp];
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
+    const uint2 pix = {pix_min.x + tx, pix_min.y + ty};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const uint32_t n = pool.count[tile];
+    if (n == 0) return;
+    const uint32_t dbase = pool.dirbase[tile];
+    const size_t plane = (size_t)H * W;
+    const bool rows16 = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0);
+    const int woff = warp * 32 + lane;
+
+    // ---- CTA prologue: directory + (id, mask) records of the tile list -> shared memory; background flag
+    const uint32_t ncache = min(n, (uint32_t)kMetaCap);
+    for (uint32_t k = tid; k * kChunkEntries < ncache; k += kThreads) Cdir[k] = chunk_of(pool, dbase, (int)k);
+    int bg_nonzero = 0;
+    for (int ch = tid; ch < C; ch += kThreads) bg_nonzero |= (bg_color[ch] != 0.f);
+    bg_nonzero = __syncthreads_or(bg_nonzero);   // also orders the Cdir stores
+    for (uint32_t e = tid; e < ncache; e += kThreads)
+        MetaS[e] = __ldg(&pool.chunks[Cdir[e / kChunkEntries]].meta[e & (kChunkEntries - 1)]);
+    __syncthreads();
+    auto chunk_ptr = [&](uint32_t e) -> const WChunk* {
+        return pool.chunks + (e < ncache ? Cdir[e / kChunkEntries] : chunk_of(pool, dbase, (int)(e / kChunkEntries)));
+    };
+    auto meta_of = [&](uint32_t e) -> uint2 {
+        return e < ncache ? MetaS[e] : __ldg(&chunk_ptr(e)->meta[e & (kChunkEntries - 1)]);
+    };
+
+    // background term of the own pixel over all channels (backward.cu:527-529); zero background: term vanishes
+    float bgdot = 0.f;
+    if (inside && bg_nonzero)
+        for (int ch = 0; ch < C; ch++) bgdot += bg_color[ch] * __ldg(dL_dpixels + (size_t)ch * plane + pix_id);
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    float last_alpha = 0.f, s_last = 0.f, A = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const int nslab = (C + CK - 1) / CK;
+    float (*S)[32] = reinterpret_cast<float (*)[32]>(&ws.DS[0][0][0]);
+
+    // dL slab [CK ch][32 px of this strip]: 4 x cp.async(16 B) per lane
+    auto dissue = [&](int sl, int buf) {
+#pragma unroll
+        for (int i = 0; i < CK / 4; i++) {
+            const int chl = (lane >> 3) + 4 * i;
+            const int ch = sl * CK + chl;
+            const int pc = lane & 7;  // 16-byte piece: tile row pc>>2 of the strip, columns (pc&3)*4..
+            const uint32_t y = pix_min.y + 2 * warp + (pc >> 2);
+            const uint32_t x = pix_min.x + (pc & 3) * 4;
+            const bool rowin = ch < C && y < (uint32_t)H;
+            const float* src = dL_dpixels + (size_t)ch * plane + (size_t)W * y + x;
+            if (rows16) {
+                const bool ok = rowin && x + 4 <= (uint32_t)W;
+                cp_async16(&ws.DS[buf][chl][pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
+            } else {  // image rows not 16-byte aligned: plain loads, ordered by the warp barrier of the slab loop
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    ws.DS[buf][chl][pc * 4 + u] = (rowin && x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    uint32_t cursor = n;  // tile-list entries [0, cursor) are still to be visited (back to front)
+    while (cursor > 0) {
+        // ---- gather the next <= 32 entries of THIS strip, walking the tile list backwards.  Slot 0 = furthest back.
+        int cnt = 0;
+        while (cnt < 32 && cursor > 0) {
+            const bool valid = (uint32_t)lane < cursor;
+            const uint32_t e = valid ? cursor - 1 - (uint32_t)lane : 0u;
+            const uint2 mt = valid ? meta_of(e) : make_uint2(0u, 0u);
+            const bool bit = valid && ((mt.y >> warp) & 1u);
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            const int room = 32 - cnt;
+            const int nset = __popc(bal);
+            const int rank = __popc(bal & ((1u << lane) - 1u));
+            if (bit && rank < room) {
+                const int slot = cnt + rank;
+                const WChunk* ck = chunk_ptr(e);
+                ws.Wrow[slot] = &ck->w[e & (kChunkEntries - 1)][0];
+                ws.Gid[slot] = mt.x;
+                const float4* rp = reinterpret_cast<const float4*>(rec + mt.x);
+                ws.RecA[slot] = __ldg(rp);
+                ws.RecB[slot] = __ldg(rp + 1);
+            }
+            if (nset <= room) {
+                cursor -= min(32u, cursor);
+                cnt += nset;
+            } else {  // segment full: resume right after the last entry taken
+                const int last_lane = __ffs(__ballot_sync(0xffffffffu, bit && rank == room - 1)) - 1;
+                cursor -= (uint32_t)(last_lane + 1);
+                cnt = 32;
+            }
+        }
+        __syncwarp();
+        if (cnt == 0) break;
+
+        // ---- s-pass: S[px][entry] = sum_ch dL[px][ch] * F[entry][ch]
+        float2 acc[8][2];  // [px][entry pair]
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+        float4 fpre[CK / 4];
+        const float* frow = features + (size_t)ws.Gid[min(lane, cnt - 1)] * C;
+        auto fload = [&](int sl) {
+#pragma unroll
+            for (int q = 0; q < CK / 4; q++) {
+                const int chb = sl * CK + q * 4;
+                fpre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < cnt) {
+                    if (VEC && chb + 4 <= C) fpre[q] = __ldg(reinterpret_cast<const float4*>(frow + chb));
+                    else {
+                        if (chb < C) fpre[q].x = __ldg(frow + chb);
+                        if (chb + 1 < C) fpre[q].y = __ldg(frow + chb + 1);
+                        if (chb + 2 < C) fpre[q].z = __ldg(frow + chb + 2);
+                        if (chb + 3 < C) fpre[q].w = __ldg(frow + chb + 3);
+                    }
+                }
+            }
+        };
+        auto fstore = [&](int buf) {  // lane = entry: conflict-free for every channel row
+#pragma unroll
+            for (int q = 0; q < CK / 4; q++) {
+                ws.FT[buf][q * 4 + 0][lane] = fpre[q].x;
+                ws.FT[buf][q * 4 + 1][lane] = fpre[q].y;
+                ws.FT[buf][q * 4 + 2][lane] = fpre[q].z;
+                ws.FT[buf][q * 4 + 3][lane] = fpre[q].w;
+            }
+        };
+        fload(0);
+        dissue(0, 0);
+        fstore(0);
+        if (nslab > 1) fload(1);
+        for (int sl = 0; sl < nslab; sl++) {
+            const int buf = sl & 1;
+            if (sl + 1 < nslab) { dissue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();  // FT[buf] stored by every lane, DS[buf] landed
+#pragma unroll 8
+            for (int k = 0; k < CK; k++) {
+                const float4 d0 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8 + 4]);
+                const float4 f0 = *reinterpret_cast<const float4*>(&ws.FT[buf][k][eg * 4]);
+                const float2 fa = make_float2(f0.x, f0.y), fb = make_float2(f0.z, f0.w);
+                const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float2 d2 = make_float2(d[i], d[i]);
+                    acc[i][0] = ffma2(fa, d2, acc[i][0]);
+                    acc[i][1] = ffma2(fb, d2, acc[i][1]);
+                }
+            }
+            __syncwarp();  // every lane is done with DS[buf] / FT[buf]
+            if (sl + 1 < nslab) {
+                fstore(buf ^ 1);
+                if (sl + 2 < nslab) fload(sl + 2);
+            }
+        }
+        // ---- park S[entry][px] in the (now free) dL slab region; 16-byte chunk c of row r sits at chunk c ^ (r >> 2)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = eg * 4 + j;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+            *reinterpret_cast<float4*>(&S[r][((2 * pg) ^ eg) * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(&S[r][((2 * pg + 1) ^ eg) * 4]) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncwarp();
+
+        // ---- back-to-front chain over the segment (backward.cu:477-550 in dot-product form); slot 0 is the
+        // furthest-back entry.  The own-pixel weights are prefetched two entries ahead.  The six per-Gaussian sums
+        // over the strip's 32 pixels go through shared memory instead of a shuffle butterfly (ncu: the butterfly was
+        // 62 of ~190 instructions per entry): every lane parks its six terms of up to 5 entries as rows of the (idle)
+        // feature-slab buffer, then lane r adds up row r with 8 x LDS.128 and issues that row's one red.global.
+        constexpr int RP = 36, RG = 5;  // row pitch (floats), entries per flush: 30 rows x 144 B <= sizeof(FT)
+        float* RB = &ws.FT[0][0][0];
+        int nbuf = 0;
+        float wn0 = __ldg(ws.Wrow[0] + woff);
+        float wn1 = cnt > 1 ? __ldg(ws.Wrow[1] + woff) : 0.f;
+        for (int li = 0; li < cnt; li++) {
+            const float w = wn0;
+            wn0 = wn1;
+            if (li + 2 < cnt) wn1 = __ldg(ws.Wrow[li + 2] + woff);
+            const float sdot = S[li][(((lane >> 2) ^ (li >> 2)) << 2) | (lane & 3)];
+            const float4 a = ws.RecA[li], con_o = ws.RecB[li];
+            float gv[6];
+#pragma unroll
+            for (int v = 0; v < 6; v++) gv[v] = 0.f;
+            if (w != 0.f) {
+                const float2 d = {a.x - pixf.x, a.y - pixf.y};
+                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                const float G = exp(power);
+                const float alpha = min(0.99f, con_o.w * G);
+                T = T / (1.f - alpha);
+                A = last_alpha * s_last + (1.f - last_alpha) * A;
+                s_last = sdot;
+                float dL_dalpha = (sdot - A) * T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                const float dL_dG = con_o.w * dL_dalpha;
+                const float gdx = G * d.x, gdy = G * d.y;
+                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                gv[1] = dL_dG * dG_ddely * ddely_dy;
+                gv[2] = -0.5f * gdx * d.x * dL_dG;
+                gv[3] = -0.5f * gdx * d.y * dL_dG;
+                gv[4] = -0.5f * gdy * d.y * dL_dG;
+                gv[5] = G * dL_dalpha;
+            }
+#pragma unroll
+            for (int v = 0; v < 6; v++) RB[(nbuf * 6 + v) * RP + lane] = gv[v];
+            nbuf++;
+            if (nbuf == RG || li == cnt - 1) {
+                __syncwarp();
+                if (lane < nbuf * 6) {
+                    const float4* row = reinterpret_cast<const float4*>(RB + lane * RP);
+                    float4 t = row[0];
+#pragma unroll
+                    for (int q = 1; q < 8; q++) {
+                        const float4 u = row[q];
+                        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                    }
+                    const float tot = (t.x + t.y) + (t.z + t.w);
+                    const int slot = lane / 6, comp = lane - slot * 6;
+                    const size_t id = ws.Gid[li - (nbuf - 1) + slot];
+                    float* dst = comp < 2 ? dL_dmean2D + id * 3 + comp
+                               : comp < 5 ? dL_dconic2D + id * 4 + (comp == 4 ? 3 : comp - 2)
+                                          : dL_dopacity + id;
+                    red_add_f32(dst, tot);
+                }
+                __syncwarp();
+                nbuf = 0;
+            }
+        }
+        __syncwarp();  // the next segment's gather / dL slab overwrite Gid, Wrow, Rec and S
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 size_t pool_bytes(int tiles, uint32_t chunks, int64_t R, PoolView* v, void* base) {
     size_t off = 0;
@@ -1067,6 +1314,7 @@ static int launch_forward_gemm(sgb_ctx* ctx, const sgb_view_inputs& in, ImgView 
     const int tiles = num_tiles(in);
     const int chunks = (in.C + 63) / 64;
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
+    if (vec && blend_mma_enabled()) return launch_forward_mma(ctx, in, im, colors, out_color, pv, s);  // opt-in experiment
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
     if (vec) {
@@ -1093,11 +1341,12 @@ static inline PoolHdr* pinned_hdr(sgb_ctx* ctx, int view_slot) {
     return reinterpret_cast<PoolHdr*>(reinterpret_cast<char*>(ctx->pinned) + 8 * kMaxBatch) + view_slot;
 }
 
-// Alpha pass + forward GEMM of one view into a pool slot; no stream sync.  The forward GEMM is enqueued before the
-// pool-size check is read back (a too-small pool only yields garbage pixels — every chunk index is clamped into the
-// pool — and the view is redone): the GPU never idles between the two kernels.
-int blend_forward_v3_enqueue(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
-                             ImgView im, const float* colors, float* out_color, cudaStream_t s) {
+// Alpha pass of one view into a pool slot; no stream sync (the pool header is copied to pinned slot `view_slot`).
+// The forward GEMM is launched by blend_forward_v3_gemm once blend_forward_v3_finish has validated the slot: the
+// host blocks only for the alpha pass (not for the GEMM), so the caller keeps enqueueing the rest of its step
+// while the GEMM runs.
+int blend_forward_v3_alpha(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
+                           ImgView im, cudaStream_t s) {
     const int tiles = num_tiles(in);
     PoolSlot* sl = pool_acquire(ctx, b);
     uint64_t want = pool_first_guess(ctx, tiles, R);
@@ -1110,14 +1359,21 @@ int blend_forward_v3_enqueue(sgb_ctx* ctx, int view_slot, const sgb_view_inputs&
     pool_bytes(tiles, chunks, R, &pv, sl->mem.p);
     rc = launch_alpha_pass(ctx, in, g, b, im, nullptr, pv, s);
     if (rc) return rc;
-    rc = launch_forward_gemm(ctx, in, im, colors, out_color, pv, s);
-    if (rc) return rc;
     SGB_CUDA(cudaMemcpyAsync(pinned_hdr(ctx, view_slot), pv.hdr, sizeof(PoolHdr), cudaMemcpyDeviceToHost, s));
     return SGB_OK;
 }
 
+int blend_forward_v3_gemm(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, BinView b, ImgView im,
+                          const float* colors, float* out_color, cudaStream_t s) {
+    PoolSlot* sl = pool_find(ctx, in, R, b);
+    if (!sl) { set_error("forward GEMM without validated weight rows"); return SGB_E_INVALID; }
+    PoolView pv;
+    pool_bytes(num_tiles(in), sl->chunks, R, &pv, sl->mem.p);
+    return launch_forward_gemm(ctx, in, im, colors, out_color, pv, s);
+}
+
 // After the stream sync: 0 = the view is done (slot validated), 1 = the pool overflowed — the slot was grown to the
-// real demand (the counter keeps counting past capacity) and the caller enqueues the view again; < 0 error.
+// real demand (the counter keeps counting past capacity) and the caller runs the alpha pass again; < 0 error.
 int blend_forward_v3_finish(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, BinView b) {
     PoolSlot* sl = nullptr;
     for (PoolSlot& c : ctx->pools)
@@ -1194,23 +1450,29 @@ int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, 
     if (rc) return rc;
     const int tiles = num_tiles(in);
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
+    // SGB_CHAIN_V3=1 selects the first-generation CTA-synchronous kernel (kept for A/B measurements)
+    static const bool use_v3 = [] { const char* e = getenv("SGB_CHAIN_V3"); return e && e[0] == '1'; }();
     const size_t smem_g = sizeof(float) * (8 * kSeg * 32 + 2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
+    const size_t smem_w = sizeof(ChainWarpSmem) * (kThreads / 32);
     static DeviceOnce attr_set;
     if (attr_set.first_use_on_device()) {
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         SGB_CUDA(cudaFuncSetAttribute(chain_backward_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        SGB_CUDA(cudaFuncSetAttribute(chain_backward_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     }
     StageTimer t(ctx, ST_BLEND_BWD, s);
     ctx->launches += 1;
-    if (vec)
-        chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                        im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
-                                                                        dL_dopacity);
-    else
-        chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(in.W, in.H, in.C, in.background, g.rec, colors,
-                                                                         im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic,
-                                                                         dL_dopacity);
-    SGB_LAUNCH_CHECK("chain_backward_gemm_kernel", in.debug, s);
+#define SGB_CHAIN_ARGS in.W, in.H, in.C, in.background, g.rec, colors, im.final_T, dL_dpix, pv, dL_dmean2D, dL_dconic, dL_dopacity
+    if (use_v3) {
+        if (vec) chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(SGB_CHAIN_ARGS);
+        else chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(SGB_CHAIN_ARGS);
+    } else {
+        if (vec) chain_backward_warp_kernel<true><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS);
+        else chain_backward_warp_kernel<false><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS);
+    }
+#undef SGB_CHAIN_ARGS
+    SGB_LAUNCH_CHECK("chain backward kernel", in.debug, s);
     return SGB_OK;
 }
 

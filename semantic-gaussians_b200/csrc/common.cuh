@@ -106,7 +106,7 @@ namespace sgb {
 // caller's stream; sgb_profile_read() sums the pairs recorded since the last read.
 enum Stage {
     ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
-    ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_TRANSPOSE, ST_FUSION_GATHER, ST_ALPHA, ST_DFEATURE,
+    ST_BLEND_BWD, ST_GEOM_BWD, ST_FUSION_PROJECT, ST_FUSION_SORT, ST_FUSION_GATHER, ST_ALPHA, ST_DFEATURE,
     ST_COUNT
 };
 constexpr int kProfRing = 320;
@@ -204,12 +204,16 @@ int launch_blend_forward(const sgb_view_inputs& in, GeomView g, BinView b, ImgVi
 int launch_blend_backward(const sgb_view_inputs& in, GeomView g, BinView b, ImgView im, const float* colors,
                           const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, cudaStream_t s);
-// C > 4 blend of one view, split so that a batch can enqueue all its views before the one stream sync:
-//   enqueue  alpha pass + forward GEMM into a weight-pool slot (no sync; pool header -> pinned slot `view_slot`)
-//   finish   after the stream was synchronised: 0 = done, 1 = the pool overflowed (slot grown: enqueue again)
-int blend_forward_v3_enqueue(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
-                             ImgView im, const float* colors, float* out_color, cudaStream_t s);
+// C > 4 forward blend of one view, split so that a batch can enqueue the alpha passes of all its views before the
+// one stream sync that validates their weight pools:
+//   alpha    alpha pass into a weight-pool slot (no sync; pool header -> pinned slot `view_slot`)
+//   finish   after the stream was synchronised: 0 = slot valid, 1 = the pool overflowed (slot grown: alpha again)
+//   gemm     forward GEMM from the validated slot
+int blend_forward_v3_alpha(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b,
+                           ImgView im, cudaStream_t s);
 int blend_forward_v3_finish(sgb_ctx* ctx, int view_slot, const sgb_view_inputs& in, int64_t R, BinView b);
+int blend_forward_v3_gemm(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, BinView b, ImgView im,
+                          const float* colors, float* out_color, cudaStream_t s);
 // backward of one view in two halves (a batch runs all dL/dfeature kernels first, records the feature-gradient
 // event, then the chain kernels): `prepare` finds or rebuilds the view's weight rows.
 int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,

@@ -3,12 +3,18 @@
 // fusion.py:127-148.  The reference does this per view on the CPU in numpy — GPU->CPU copies of
 // xyz, the view matrix and the rendered depth, a fancy-index gather of a (C,h,w) map for ALL P
 // points, then a P x C host->device copy.  Here one view is: projection + visibility test on the
-// device (float64 like numpy), one tiled transpose of the feature map to pixel-major so that a
-// Gaussian's C-vector is one contiguous row, and a gather-accumulate into the fp32 sums.
+// device (float64 like numpy), a counting sort of the visible Gaussians by pixel, and one fused
+// gather-accumulate kernel that reads the PLANAR (C,h,w) map directly: a warp takes 32 pixel-sorted
+// Gaussians, so for every channel its 32 two-byte reads fall into a few neighbouring sectors of that
+// channel plane, stages [32 Gaussians][128 channels] in shared memory and adds each row to the fp32
+// sums as contiguous 128-byte pieces.  (Round 1 transposed the whole map to pixel-major first: 630 MB
+// of traffic per view that the algorithm does not need — the map is now read at most once, and only
+// where visible Gaussians land.)
 //
 // Numerics: projection in float64 with numpy's promotion rules (float32 inputs widened), pixel =
 // round-half-to-even; the per-Gaussian sums add the views in call order in fp32 exactly like
 // `_features_semantic[mask] += features_mapping[mask]`, so they are bit-identical to the reference.
+#include <cub/cub.cuh>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -101,15 +107,21 @@ __global__ void fusion_map_kernel(sgb_fusion_view v, const double* zbuf, long lo
     mapping[3 * (size_t)i + 2] = pix >= 0 ? 1 : 0;
 }
 
+// Visibility of every Gaussian in this view; count += 1 for the visible ones (fusion.py:143); per-pixel histogram of
+// the visible Gaussians (input of the counting sort).
 __global__ void fusion_pix_kernel(sgb_fusion_view v, const double* zbuf, int* __restrict__ pix_of,
-                                  float* __restrict__ count, int* __restrict__ n_visible) {
+                                  float* __restrict__ count, int* __restrict__ n_visible,
+                                  uint32_t* __restrict__ hist) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int pix = -1;
     if (i < v.P) {
         Proj p;
         pix = visible_pixel(v, zbuf, i, p);
         pix_of[i] = pix;
-        if (pix >= 0) count[i] += 1.0f;  // gaussians._times[mask] += 1, fusion.py:143
+        if (pix >= 0) {
+            count[i] += 1.0f;  // gaussians._times[mask] += 1, fusion.py:143
+            atomicAdd(hist + pix, 1u);
+        }
     }
     if (n_visible) {
         unsigned m = __ballot_sync(0xffffffffu, pix >= 0);
@@ -117,74 +129,64 @@ __global__ void fusion_pix_kernel(sgb_fusion_view v, const double* zbuf, int* __
     }
 }
 
-// (C, npix) -> (npix, C) tiled transpose, 32x32 tiles through shared memory.
-template <typename T>
-__global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int npix) {
-    __shared__ T tile[32][33];
-    const int px0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int c = c0 + r, px = px0 + threadIdx.x;
-        if (c < C && px < npix) tile[r][threadIdx.x] = in[(size_t)c * npix + px];
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int px = px0 + r, c = c0 + threadIdx.x;
-        if (c < C && px < npix) out[(size_t)px * C + c] = tile[threadIdx.x][r];
-    }
+// Counting sort, scatter step: `cursor` holds the exclusive scan of the histogram and is advanced atomically.  The
+// order inside a pixel is arbitrary — every Gaussian owns its own accumulator row.
+__global__ void fusion_scatter_kernel(int P, const int* __restrict__ pix_of, uint32_t* __restrict__ cursor,
+                                      uint32_t* __restrict__ sorted_ids, uint32_t* __restrict__ sorted_pix) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int pix = pix_of[i];
+    if (pix < 0) return;
+    const uint32_t pos = atomicAdd(cursor + pix, 1u);
+    sorted_ids[pos] = (uint32_t)i;
+    sorted_pix[pos] = (uint32_t)pix;
 }
 
 __device__ __forceinline__ float to_f32(__half h) { return __half2float(h); }
 __device__ __forceinline__ float to_f32(float f) { return f; }
 
-// One warp per Gaussian (grid-stride): feat_sum[g, :] += featT[pix(g), :] for visible g.
-// fp16 maps: 64 channels x 64 pixels per CTA, every global access is a 4-byte pair (128 B per warp row instead
-// of the 64 B of the element-wise kernel above).  Shared cell (r, j) = the pixel pair (2j, 2j+1) of channel r.
-// Requires even npix and C and 4-byte aligned bases.
-__global__ void __launch_bounds__(256) transpose_half2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                                                              int C, int npix) {
-    __shared__ uint32_t tile[64][33];
-    const int px0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int r = ty; r < 64; r += 8) {
-        const int c = c0 + r, px = px0 + 2 * tx;
-        uint32_t v = 0u;
-        if (c < C && px < npix) v = __ldg(reinterpret_cast<const uint32_t*>(in + (size_t)c * npix + px));
-        tile[r][tx] = v;
-    }
-    __syncthreads();
-    const int c = c0 + 2 * tx;
-    if (c >= C) return;
-    for (int r = ty; r < 64; r += 8) {
-        const int px = px0 + r;
-        if (px >= npix) break;
-        const uint32_t a = tile[2 * tx][r >> 1], b = tile[2 * tx + 1][r >> 1];
-        const uint32_t lo = (r & 1) ? (a >> 16) : (a & 0xFFFFu), hi = (r & 1) ? (b >> 16) : (b & 0xFFFFu);
-        *reinterpret_cast<uint32_t*>(out + (size_t)px * C + c) = lo | (hi << 16);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) fusion_gather_kernel(int P, int C, const int* __restrict__ pix_of,
-                                                            const T* __restrict__ featT,
-                                                            float* __restrict__ feat_sum) {
-    const int lane = threadIdx.x & 31;
+// feat_sum[g, :] += map[:, pix(g)] for the visible Gaussians, in pixel order.  Warp = 32 consecutive entries of the
+// pixel-sorted list; CHP channels per pass through a private shared-memory tile [32][CHP] (odd word pitch: the
+// per-lane row writes of the load phase and the per-row reads of the accumulate phase are both conflict-free).
+template <typename T, int CHP>
+__global__ void __launch_bounds__(256) fusion_gather_sorted_kernel(const int* __restrict__ n_visible, int C, int npix,
+                                                                   const uint32_t* __restrict__ sorted_ids,
+                                                                   const uint32_t* __restrict__ sorted_pix,
+                                                                   const T* __restrict__ fm,
+                                                                   float* __restrict__ feat_sum) {
+    constexpr int PITCH = CHP + (sizeof(T) == 2 ? 2 : 1);  // elements; 65 32-bit words either way
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * PITCH;
+    const int nvis = *n_visible;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < P; g += warps_total) {
-        const int pix = pix_of[g];
-        if (pix < 0) continue;
-        const T* src = featT + (size_t)pix * C;
-        float* dst = feat_sum + (size_t)g * C;
-        if ((C & 3) == 0) {
-            for (int k = lane * 4; k < C; k += 128) {
-                float4 acc = *reinterpret_cast<const float4*>(dst + k);
-                acc.x += to_f32(src[k]);
-                acc.y += to_f32(src[k + 1]);
-                acc.z += to_f32(src[k + 2]);
-                acc.w += to_f32(src[k + 3]);
-                *reinterpret_cast<float4*>(dst + k) = acc;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b * 32 < nvis; b += warps_total) {
+        const int j = b * 32 + lane;
+        const bool valid = j < nvis;
+        const uint32_t gid = valid ? sorted_ids[j] : 0u;
+        uint32_t pix = valid ? sorted_pix[j] : 0u;
+        pix = valid ? pix : __shfl_sync(0xffffffffu, pix, 0);  // idle lanes re-read lane 0's pixel (in range, cached)
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const T* src = fm + pix;
+        for (int c0 = 0; c0 < C; c0 += CHP) {
+            const int nc = min(CHP, C - c0);
+            // load phase: lane = Gaussian, one element per channel plane
+#pragma unroll 8
+            for (int c = 0; c < CHP; c++)
+                if (c < nc) tile[lane * PITCH + c] = src[(size_t)(c0 + c) * npix];
+            __syncwarp();
+            // accumulate phase: row by row, lanes along the channels (128-byte pieces of the fp32 row)
+            for (int g = 0; g < 32; g++) {
+                if (!((vmask >> g) & 1u)) break;  // valid lanes are a prefix
+                const uint32_t gg = __shfl_sync(0xffffffffu, gid, g);
+                float* dst = feat_sum + (size_t)gg * C + c0;
+#pragma unroll
+                for (int k = 0; k < CHP / 32; k++) {
+                    const int c = lane + 32 * k;
+                    if (c < nc) dst[c] += to_f32(tile[g * PITCH + c]);
+                }
             }
-        } else {
-            for (int k = lane; k < C; k += 32) dst[k] += to_f32(src[k]);
+            __syncwarp();
         }
     }
 }
@@ -268,42 +270,59 @@ extern "C" int sgb_fusion_accumulate(sgb_ctx* ctx, const sgb_fusion_view* v, con
     if (n_visible_dev) SGB_CUDA(cudaMemsetAsync(n_visible_dev, 0, sizeof(int32_t), s));
     if (v->P == 0) return SGB_OK;
     const size_t npix = (size_t)v->w * v->h;
-    const size_t esz = feat_dtype == SGB_FEAT_F16 ? 2 : 4;
-    const size_t tbytes = align_up(npix * C * esz);
-    const size_t pbytes = align_up(sizeof(int) * (size_t)v->P);
+    // scratch: pix_of [P] | sorted ids [P] | sorted pix [P] | histogram / cursor [npix] | n_visible | cub temp
+    size_t scan_tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)npix, s);
+    const size_t parr = align_up(sizeof(int) * (size_t)v->P), harr = align_up(sizeof(uint32_t) * npix);
     double* zbuf; char* extra;
-    rc = prepare_zbuf(ctx, *v, tbytes + pbytes, &zbuf, &extra, s);
+    rc = prepare_zbuf(ctx, *v, 3 * parr + 2 * harr + 256 + align_up(scan_tmp), &zbuf, &extra, s);
     if (rc) return rc;
-    void* featT = extra;
-    int* pix_of = (int*)(extra + tbytes);
-
+    int* pix_of = (int*)extra;
+    uint32_t* sorted_ids = (uint32_t*)(extra + parr);
+    uint32_t* sorted_pix = (uint32_t*)(extra + 2 * parr);
+    uint32_t* hist = (uint32_t*)(extra + 3 * parr);
+    uint32_t* cursor = (uint32_t*)(extra + 3 * parr + harr);
+    int* nvis_own = (int*)(extra + 3 * parr + 2 * harr);
+    void* cub_tmp = extra + 3 * parr + 2 * harr + 256;
+    int* nvis = n_visible_dev ? n_visible_dev : nvis_own;
+    if (!n_visible_dev) SGB_CUDA(cudaMemsetAsync(nvis_own, 0, sizeof(int), s));
     {
         StageTimer t(ctx, ST_FUSION_PROJECT, s);
-        fusion_pix_kernel<<<(v->P + 255) / 256, 256, 0, s>>>(*v, zbuf, pix_of, count, n_visible_dev);
+        SGB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * npix, s));
+        fusion_pix_kernel<<<(v->P + 255) / 256, 256, 0, s>>>(*v, zbuf, pix_of, count, nvis, hist);
         SGB_LAUNCH_CHECK("fusion_pix_kernel", 0, s);
     }
-    dim3 tgrid((unsigned)((npix + 31) / 32), (unsigned)((C + 31) / 32)), tblock(32, 8);
-    const int gblocks = 148 * 8;
     {
-        StageTimer t(ctx, ST_FUSION_TRANSPOSE, s);
-        const bool pairs = feat_dtype == SGB_FEAT_F16 && (npix % 2 == 0) && (C % 2 == 0) &&
-                           ((reinterpret_cast<uintptr_t>(features) & 3) == 0) && ((reinterpret_cast<uintptr_t>(featT) & 3) == 0);
-        if (pairs)
-            transpose_half2_kernel<<<dim3((unsigned)((npix + 63) / 64), (unsigned)((C + 63) / 64)), tblock, 0, s>>>(
-                (const __half*)features, (__half*)featT, C, (int)npix);
-        else if (feat_dtype == SGB_FEAT_F16)
-            transpose_kernel<__half><<<tgrid, tblock, 0, s>>>((const __half*)features, (__half*)featT, C, (int)npix);
-        else
-            transpose_kernel<float><<<tgrid, tblock, 0, s>>>((const float*)features, (float*)featT, C, (int)npix);
+        StageTimer t(ctx, ST_FUSION_SORT, s);
+        SGB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, scan_tmp, hist, cursor, (int)npix, s));
+        fusion_scatter_kernel<<<(v->P + 255) / 256, 256, 0, s>>>(v->P, pix_of, cursor, sorted_ids, sorted_pix);
+        SGB_LAUNCH_CHECK("fusion_scatter_kernel", 0, s);
+        ctx->lib_launches += 1;
     }
     {
         StageTimer t(ctx, ST_FUSION_GATHER, s);
-        if (feat_dtype == SGB_FEAT_F16)
-            fusion_gather_kernel<__half><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const __half*)featT, feat_sum);
-        else
-            fusion_gather_kernel<float><<<gblocks, 256, 0, s>>>(v->P, C, pix_of, (const float*)featT, feat_sum);
+        const int gblocks = 148 * 3;
+        if (feat_dtype == SGB_FEAT_F16) {
+            constexpr int CHP = 128;
+            const size_t smem = 8 * 32 * (CHP + 2) * sizeof(__half);
+            static DeviceOnce once;
+            if (once.first_use_on_device())
+                SGB_CUDA(cudaFuncSetAttribute(fusion_gather_sorted_kernel<__half, CHP>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fusion_gather_sorted_kernel<__half, CHP><<<gblocks, 256, smem, s>>>(nvis, C, (int)npix, sorted_ids, sorted_pix,
+                                                                               (const __half*)features, feat_sum);
+        } else {
+            constexpr int CHP = 64;
+            const size_t smem = 8 * 32 * (CHP + 1) * sizeof(float);
+            static DeviceOnce once;
+            if (once.first_use_on_device())
+                SGB_CUDA(cudaFuncSetAttribute(fusion_gather_sorted_kernel<float, CHP>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fusion_gather_sorted_kernel<float, CHP><<<gblocks, 256, smem, s>>>(nvis, C, (int)npix, sorted_ids, sorted_pix,
+                                                                              (const float*)features, feat_sum);
+        }
+        SGB_LAUNCH_CHECK("fusion_gather_sorted_kernel", 0, s);
     }
-    SGB_LAUNCH_CHECK("fusion_gather_kernel", 0, s);
     ctx->launches += 3;
     return SGB_OK;
 }

@@ -157,6 +157,126 @@ def _backward_impl(background, means3D, radii, colors, scales, rotations, scale_
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 
+# ------------------------------------------------------------------------------------------------ batched views
+def _ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def _camera_array(settings_list, dev, keep):
+    cams = (_lib.Camera * len(settings_list))()
+    for i, rs in enumerate(settings_list):
+        v, p, c = _f32(rs.viewmatrix, dev, "viewmatrix"), _f32(rs.projmatrix, dev, "projmatrix"), _f32(rs.campos, dev, "campos")
+        keep += [v, p, c]
+        cams[i] = _lib.Camera(viewmatrix=v.data_ptr(), projmatrix=p.data_ptr(), campos=c.data_ptr(),
+                              tan_fovx=float(rs.tanfovx), tan_fovy=float(rs.tanfovy))
+    return cams
+
+
+def _check_batch_settings(settings_list):
+    rs0 = settings_list[0]
+    if not (1 <= len(settings_list) <= _lib.MAX_BATCH):
+        raise ValueError(f"a batch holds 1..{_lib.MAX_BATCH} views, got {len(settings_list)}")
+    for rs in settings_list[1:]:
+        same = (rs.image_height == rs0.image_height and rs.image_width == rs0.image_width and
+                rs.scale_modifier == rs0.scale_modifier and rs.sh_degree == rs0.sh_degree and
+                bool(rs.prefiltered) == bool(rs0.prefiltered) and rs.bg is rs0.bg and
+                getattr(rs, "num_channels", 3) == getattr(rs0, "num_channels", 3))
+        if not same:
+            raise ValueError("the views of a batch must share image size, background tensor, scale modifier, SH degree "
+                             "and channel count (only the cameras differ)")
+    return rs0
+
+
+def _forward_batch_impl(want_depth: bool, settings_list, means3D, colors, opacity, scales, rotations, cov3D_precomp,
+                        sh, num_channels):
+    """V views of the same Gaussians through sgb_forward_geometry_batch / sgb_forward_render_batch: one stream
+    sync for all instance counts, one for all weight-pool checks.  Returns per-view lists."""
+    lib = _lib.load()
+    rs0 = _check_batch_settings(settings_list)
+    V = len(settings_list)
+    inp, keep, dev = _make_inputs(rs0.bg, means3D, colors, opacity, scales, rotations, rs0.scale_modifier,
+                                  cov3D_precomp, rs0.viewmatrix, rs0.projmatrix, rs0.tanfovx, rs0.tanfovy,
+                                  rs0.image_height, rs0.image_width, sh, rs0.sh_degree, rs0.campos, rs0.prefiltered,
+                                  getattr(rs0, "debug", False), num_channels)
+    P, H, W, Cn = inp.P, inp.H, inp.W, inp.C
+    if P == 0:
+        raise ValueError("batched rasterization of an empty scene: use the single-view call")
+    u8 = dict(dtype=torch.uint8, device=dev)
+    keep_list = [keep]
+    with torch.cuda.device(dev):
+        stream, ctx = _stream_ctx(dev)
+        cams = _camera_array(settings_list, dev, keep_list)
+        out_color = [torch.empty((Cn, H, W), dtype=torch.float32, device=dev) for _ in range(V)]
+        out_depth = [torch.empty((1, H, W), dtype=torch.float32, device=dev) for _ in range(V)] if want_depth else None
+        radii = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(V)]
+        geom = [torch.empty((lib.sgb_geometry_bytes(P),), **u8) for _ in range(V)]
+        img = [torch.empty((lib.sgb_image_bytes(W, H),), **u8) for _ in range(V)]
+        R = (C.c_int64 * V)()
+        _lib.check(lib.sgb_forward_geometry_batch(ctx, C.byref(inp), V, cams, _ptr_array([g.data_ptr() for g in geom]),
+                                                  _ptr_array([r.data_ptr() for r in radii]), R, stream),
+                   "rasterize_gaussians_batch (geometry)")
+        binning = [torch.empty((lib.sgb_binning_bytes(R[v]),), **u8) for v in range(V)]
+        _lib.check(lib.sgb_forward_render_batch(
+            ctx, C.byref(inp), V, cams, R, _ptr_array([g.data_ptr() for g in geom]),
+            _ptr_array([b.data_ptr() for b in binning]), _ptr_array([i.data_ptr() for i in img]),
+            _ptr_array([r.data_ptr() for r in radii]), _ptr_array([o.data_ptr() for o in out_color]),
+            _ptr_array([d.data_ptr() for d in out_depth]) if want_depth else None, stream),
+            "rasterize_gaussians_batch (render)")
+    del keep_list
+    return [int(R[v]) for v in range(V)], out_color, radii, geom, binning, img, out_depth
+
+
+def _backward_batch_impl(settings_list, means3D, radii, colors, scales, rotations, cov3D_precomp, dL_dout, sh,
+                         geom, R, binning, img, num_channels):
+    """sgb_backward_batch: the (P, C) colour / feature gradient accumulates over the views in ONE buffer; the small
+    per-Gaussian gradients are per view and summed here (means2D stays per view)."""
+    lib = _lib.load()
+    rs0 = settings_list[0]
+    V = len(settings_list)
+    H, W = rs0.image_height, rs0.image_width
+    inp, keep, dev = _make_inputs(rs0.bg, means3D, colors, means3D, scales, rotations, rs0.scale_modifier,
+                                  cov3D_precomp, rs0.viewmatrix, rs0.projmatrix, rs0.tanfovx, rs0.tanfovy, H, W, sh,
+                                  rs0.sh_degree, rs0.campos, False, getattr(rs0, "debug", False), num_channels)
+    P, M, Cn = inp.P, inp.M, inp.C
+    z = dict(dtype=torch.float32, device=dev)
+    # precomputed colours / features: ONE (P, C) buffer, summed over the views in place.  SH path: the per-view RGB
+    # gradient is an input of that view's SH backward (backward.cu:385-386), so every view needs its own (P, 3).
+    shared = M == 0
+    dL_dcolors = torch.zeros((P, Cn) if shared else (V, P, Cn), **z)
+    per = dict(dL_dmeans3D=(P, 3), dL_dmeans2D=(P, 3), dL_dconic=(P, 2, 2), dL_dopacity=(P, 1), dL_dcov3D=(P, 6),
+               dL_dsh=(P, M, 3), dL_dscales=(P, 3), dL_drotations=(P, 4))
+    small = {k: torch.zeros((V,) + shp, **z) for k, shp in per.items()}
+    gouts = [_f32(g, dev, "dL_dout_color") for g in dL_dout]
+    grads = (_lib.ViewGrads * V)()
+    for v in range(V):
+        grads[v] = _lib.ViewGrads(
+            dL_dmeans2D=small["dL_dmeans2D"][v].data_ptr(), dL_dconic=small["dL_dconic"][v].data_ptr(),
+            dL_dopacity=small["dL_dopacity"][v].data_ptr(),
+            dL_dcolors=(dL_dcolors if shared else dL_dcolors[v]).data_ptr(),
+            dL_dmeans3D=small["dL_dmeans3D"][v].data_ptr(), dL_dcov3D=small["dL_dcov3D"][v].data_ptr(),
+            dL_dsh=small["dL_dsh"][v].data_ptr() if M > 0 else None, dL_dscales=small["dL_dscales"][v].data_ptr(),
+            dL_drotations=small["dL_drotations"][v].data_ptr())
+    keep_list = [keep]
+    with torch.cuda.device(dev):
+        stream, ctx = _stream_ctx(dev)
+        cams = _camera_array(settings_list, dev, keep_list)
+        Rarr = (C.c_int64 * V)(*[int(r) for r in R])
+        _lib.check(lib.sgb_backward_batch(
+            ctx, C.byref(inp), V, cams, Rarr, _ptr_array([r.data_ptr() for r in radii]),
+            _ptr_array([g.data_ptr() for g in geom]), _ptr_array([b.data_ptr() for b in binning]),
+            _ptr_array([i.data_ptr() for i in img]), _ptr_array([g.data_ptr() for g in gouts]), grads, stream),
+            "rasterize_gaussians_backward_batch")
+    del keep_list
+    if not shared:
+        dL_dcolors = dL_dcolors.sum(0)
+    return (small["dL_dmeans2D"], dL_dcolors, small["dL_dopacity"].sum(0), small["dL_dmeans3D"].sum(0),
+            small["dL_dcov3D"].sum(0), small["dL_dsh"].sum(0), small["dL_dscales"].sum(0),
+            small["dL_drotations"].sum(0))
+
+
 def _mark_visible(means3D, viewmatrix, projmatrix):
     lib = _lib.load()
     dev = means3D.device
@@ -323,6 +443,77 @@ def make_module(variant: str):
         return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                          cov3Ds_precomp, raster_settings)
 
+    class _RasterizeGaussiansBatch(torch.autograd.Function):
+        """V views of the same Gaussians in one native call each way (the reference loops over
+        single-view calls in Python, eval_segmentation.py:146-157).  Outputs per view are those of
+        _RasterizeGaussians; the backward sums the per-Gaussian gradients over the views, the (P, C) feature
+        gradient in place inside the kernels."""
+
+        @staticmethod
+        def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings_list,
+                    *means2D):
+            V = len(settings_list)
+            nch = settings_list[0].num_channels if is_chn else 3
+            R, color, radii, geom, binning, img, depth = _forward_batch_impl(
+                not is_chn, settings_list, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh, nch)
+            ctx.settings_list, ctx.R, ctx.V, ctx.nch = list(settings_list), R, V, nch
+            ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, sh, *radii, *geom,
+                                  *binning, *img)
+            ctx.mark_non_differentiable(*radii)
+            if is_chn:
+                return (*color, *radii)
+            ctx.mark_non_differentiable(*depth)
+            return (*color, *radii, *depth)
+
+        @staticmethod
+        def backward(ctx, *grad_outputs):
+            V = ctx.V
+            saved = ctx.saved_tensors
+            colors_precomp, means3D, scales, rotations, cov3Ds_precomp, sh = saved[:6]
+            rest = saved[6:]
+            radii, geom, binning, img = rest[:V], rest[V:2 * V], rest[2 * V:3 * V], rest[3 * V:4 * V]
+            rs0 = ctx.settings_list[0]
+            gouts = []
+            for v in range(V):
+                g = grad_outputs[v]
+                if g is None:
+                    g = torch.zeros((ctx.nch, rs0.image_height, rs0.image_width), dtype=torch.float32,
+                                    device=means3D.device)
+                gouts.append(g)
+            (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = _backward_batch_impl(
+                ctx.settings_list, means3D, radii, colors_precomp, scales, rotations, cov3Ds_precomp, gouts, sh, geom,
+                ctx.R, binning, img, ctx.nch)
+
+            def present(t, g):
+                return g if t.numel() != 0 else None
+            return (g_means3D, present(sh, g_sh), present(colors_precomp, g_colors), g_opac, present(scales, g_scales),
+                    present(rotations, g_rot), present(cov3Ds_precomp, g_cov3D), None,
+                    *[g_means2D[v] for v in range(V)])
+
+    def rasterize_gaussians_batch(means3D, means2D_list, opacities, settings_list, shs=None, colors_precomp=None,
+                                  scales=None, rotations=None, cov3D_precomp=None):
+        """Batched counterpart of GaussianRasterizer.forward: ``settings_list`` holds one
+        GaussianRasterizationSettings per view (same image size / background tensor / channel count; only the
+        cameras differ), ``means2D_list`` one screen-space tensor per view.  Returns a list of per-view tuples
+        (color, radii[, depth]).  Batches larger than the native limit are split."""
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])
+        e = lambda t: empty if t is None else t
+        results = []
+        for lo in range(0, len(settings_list), _lib.MAX_BATCH):
+            sl = list(settings_list[lo:lo + _lib.MAX_BATCH])
+            m2 = list(means2D_list[lo:lo + _lib.MAX_BATCH])
+            out = _RasterizeGaussiansBatch.apply(means3D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
+                                                 e(cov3D_precomp), sl, *m2)
+            V = len(sl)
+            for v in range(V):
+                results.append((out[v], out[V + v]) if is_chn else (out[v], out[V + v], out[2 * V + v]))
+        return results
+
     class GaussianRasterizer(nn.Module):  # channel_rasterization/__init__.py:232-289
         def __init__(self, raster_settings):
             super().__init__()
@@ -353,4 +544,5 @@ def make_module(variant: str):
 
     GaussianRasterizationSettings.__qualname__ = "GaussianRasterizationSettings"
     GaussianRasterizer.__qualname__ = "GaussianRasterizer"
+    GaussianRasterizer.rasterize_batch = staticmethod(rasterize_gaussians_batch)
     return GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _RasterizeGaussians, _C

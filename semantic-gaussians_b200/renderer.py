@@ -93,3 +93,71 @@ def render_chn(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modif
     rendered_image, radii = rasterizer.forward(**call)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii}
+
+
+def _render_batch(variant, cameras, pc, pipe, bg_color, scaling_modifier, num_channels, override_color, override_shape,
+                  foreground, world_rotate):
+    """Shared body of render_batch / render_chn_batch: the Gaussian-side tensors are prepared ONCE (the reference's
+    per-view loop, eval_segmentation.py:146-157 / fusion.py:106-120, re-evaluates the activations for every view),
+    the views go through the batched native calls (rasterizer.rasterize_gaussians_batch)."""
+    cameras = list(cameras)
+    if not cameras:
+        return []
+    single = render if variant == "rgbd" else (
+        lambda cam, *a, **k: render_chn(cam, *a, num_channels=num_channels, **k))
+    per_view_colors = override_color is None and pipe.convert_shs_python   # python SH -> colours depend on the camera
+    if per_view_colors or pc.get_xyz.shape[0] == 0:
+        return [single(cam, pc, pipe, bg_color, scaling_modifier=scaling_modifier, override_color=override_color,
+                       override_shape=override_shape, foreground=foreground, world_rotate=world_rotate)
+                for cam in cameras]
+    pts0, common0, call = _prepare(cameras[0], pc, pipe, scaling_modifier, override_color, override_shape, foreground,
+                                   world_rotate)
+    mod = chn_rasterize if variant == "chn" else None
+    settings, points = [], []
+    for i, cam in enumerate(cameras):
+        common = dict(common0, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+                      viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center)
+        if override_shape is None and (int(cam.image_height), int(cam.image_width)) != (common0["image_height"],
+                                                                                        common0["image_width"]):
+            raise ValueError("the views of a batch must share the image size")
+        if variant == "chn":
+            settings.append(mod.GaussianRasterizationSettings(bg=bg_color, debug=bool(getattr(pipe, "debug", False)),
+                                                              num_channels=num_channels, **common))
+        else:
+            settings.append(GaussianRasterizationSettings(bg=bg_color, debug=pipe.debug, **common))
+        if i == 0:
+            points.append(pts0)
+        else:
+            p = torch.zeros_like(pts0, requires_grad=True) + 0
+            try:
+                p.retain_grad()
+            except Exception:
+                pass
+            points.append(p)
+    Rast = mod.GaussianRasterizer if variant == "chn" else GaussianRasterizer
+    outs = Rast.rasterize_batch(call["means3D"], points, call["opacities"], settings, shs=call["shs"],
+                                colors_precomp=call["colors_precomp"], scales=call["scales"],
+                                rotations=call["rotations"], cov3D_precomp=call["cov3D_precomp"])
+    res = []
+    for pts, o in zip(points, outs):
+        d = {"render": o[0], "viewspace_points": pts, "visibility_filter": o[1] > 0, "radii": o[1]}
+        if variant == "rgbd":
+            d["depth"] = o[2]
+        res.append(d)
+    return res
+
+
+def render_batch(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+                 override_shape=None, foreground=None, world_rotate=None):
+    """``[render(cam, ...) for cam in cameras]`` through the batched native path: same per-view dicts."""
+    return _render_batch("rgbd", cameras, pc, pipe, bg_color, scaling_modifier, 3, override_color, override_shape,
+                         foreground, world_rotate)
+
+
+def render_chn_batch(cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, num_channels=3,
+                     override_color=None, override_shape=None, foreground=None, world_rotate=None):
+    """``[render_chn(cam, ...) for cam in cameras]`` through the batched native path (BASELINE config K4: a rank's
+    share of a view batch).  Backward of any loss over the returned images sums the per-Gaussian gradients over the
+    views inside the kernels — one (P, C) feature-gradient buffer for the whole batch."""
+    return _render_batch("chn", cameras, pc, pipe, bg_color, scaling_modifier, num_channels, override_color,
+                         override_shape, foreground, world_rotate)
