@@ -1072,12 +1072,16 @@ def run_k5(args, rank, world, local_rank):
     maps = [torch.randn((C, hh, w), device=dev, generator=g).half() for _ in range(NM)]
     host_maps = [torch.randn((C, hh, w)).half().pin_memory() for _ in range(2)]
     bg3 = torch.zeros(3, device=dev)
-    # depth of every local view = the rasterizer's median depth at the fusion resolution (fusion.py:106-120), rendered
-    # once outside the timed region (the render itself is the K2-type path)
+    # Visibility rule.  Default: the reference's `depth: none` branch (fusion_utils.py:70-72 — every Gaussian in front of
+    # the camera and inside the cut image is visible): on a synthetic random cloud the rendered-depth test
+    # (fusion.py:106-120) leaves < 100 of 2 M Gaussians visible per view (measured), which would benchmark nothing.
+    # SGB_K5_DEPTH=render selects the rendered median depth (rendered once, outside the timed region).
+    use_render = os.environ.get("SGB_K5_DEPTH", "none") == "render"
     depth, mappers = {}, {}
     with torch.no_grad():
         for k in mine:
-            depth[k] = render(h.dev_cam(cams_np[k]), pc, Pipe, bg3, override_shape=[w, hh])["depth"][0].contiguous()
+            depth[k] = (render(h.dev_cam(cams_np[k]), pc, Pipe, bg3, override_shape=[w, hh])["depth"][0].contiguous()
+                        if use_render else None)
             mappers[k] = PointCloudToImageMapper([w, hh], 0.25, 10, cams_np[k].intrinsics(), device=dev)
     w2c = {k: torch.as_tensor(cams_np[k].world_view_transform, device=dev) for k in mine}
     fs = torch.zeros((P, C), device=dev)
@@ -1149,7 +1153,8 @@ def run_k5(args, rank, world, local_rank):
     line.update({
         "config": {"workload": cfg["workload"], "P": P, "C": C, "W": w, "H": hh, "views_per_step": VT,
                    "views_per_rank": len(mine), "feature_dtype": "float16", "visibility_threshold": 0.25, "cut_boundary": 10,
-                   "depth": "rasterizer median depth at 640x480 (fusion.py:106-120), rendered outside the timed region",
+                   "depth": "rendered median depth (fusion.py:106-120)" if use_render else
+                            "none: every Gaussian in front of the camera inside the cut image is visible (fusion_utils.py:70-72)",
                    "N_vis_per_view": {"mean": nv_mean, "min": min(nvis) if nvis else 0, "max": max(nvis) if nvis else 0},
                    "parallelism": f"views strided over {world} ranks, one all-reduce of the (P, C) sums + counts, then normalise",
                    "l2": "4 cycling 315 MB maps and a 4.1 GB accumulator: beyond L2"},

@@ -6,18 +6,18 @@
 // a 70 TFLOP/s fp32 roof, i.e. FMA-issue bound at ~0.2 of the HBM roofline.  This file measures what the mandate
 // costs: the same contraction on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) with fp32
 // accuracy recovered by the error-compensated 3 x TF32 split
-//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared,  lo = (x - hi) cleared the same way
-//     w * f  ~=  hi_w * hi_f + hi_w * lo_f + lo_w * hi_f                      (lo_w * lo_f <= 2^-20 |w f| dropped)
+//     x = hi + lo,  hi = tf32(x) (round to nearest),  lo = tf32(x - hi)       (|lo| <= 2^-12 |x|)
+//     w * f  ~=  hi_w * hi_f + hi_w * lo_f + lo_w * hi_f                      (lo_w * lo_f <= 2^-24 |w f| dropped)
 // three kind::tf32 MMAs per K block accumulating in fp32.  The legacy mma.sync path was measured first
 // (tools/microbench.cu): 277 TFLOP/s dense TF32 -> 67 TFLOP/s fp32-equivalent for the 3x split, no better than the
 // CUDA cores; only tcgen05 (1.1 PFLOP/s dense TF32) changes the picture.
 //
 // Kernel: CTA = (tile, 128-channel slice), 256 threads, 2 CTAs/SM (256 TMEM columns each: D[256 px][128 ch] as two
 // M = 128 halves).  Per batch of 16 list entries every thread moves 6 x 16 B of raw fp32 operands global ->
-// registers (one batch ahead) -> hi / lo copies in shared memory, laid out as the UMMA canonical MN-major no-swizzle
-// operand (both operands are naturally MN-major: a weight row is contiguous in pixels, a feature row in channels;
-// 16-byte chunk (4 consecutive M or N of one entry k) at (mn/4)*128 + (k%8)*16 inside a K block — layout and
-// descriptor fields validated on hardware by tools/tc_probe.cu).  One elected thread issues the 12 MMAs of a batch
+// registers (one batch ahead) -> hi / lo copies in shared memory, laid out as the UMMA canonical K-major no-swizzle
+// operand (16-byte chunk = 4 consecutive entries k of one row, 8 rows = one 128-byte core matrix; layout and
+// descriptor fields validated on hardware by tools/tc_probe.cu — both operands are naturally MN-major here, but the
+// MN-major descriptor forms produced no output in the probe, so the staging threads transpose).  One elected thread issues the 12 MMAs of a batch
 // (2 K blocks x 2 pixel halves x 3 products) and commits them to the stage's mbarrier; the epilogue reads TMEM with
 // tcgen05.ld (TMEM lane = pixel), adds T * bg and stores the planar image.
 // Reference semantics: forward.cu:355-356, 372-373 (accumulation order differs: fp32 tree inside the tensor core).
@@ -32,8 +32,8 @@ namespace {
 constexpr int kMmaThreads = 256;
 constexpr int kNch = 128;              // channels per CTA (MMA N)
 constexpr int kBatch = 16;             // list entries per pipeline stage = 2 K blocks of 8
-constexpr uint32_t kABlk = 32 * 128;   // bytes of one (K block, pixel half) operand block: 32 px groups x 128 B
-constexpr uint32_t kBBlk = (kNch / 4) * 128;
+constexpr uint32_t kABlk = 16 * 256;   // bytes of one (K block, pixel half) operand block: 16 row groups x 256 B
+constexpr uint32_t kBBlk = (kNch / 8) * 256;
 constexpr uint32_t kStageA = 2 * 2 * kABlk;   // [kb][mh]
 constexpr uint32_t kStageB = 2 * kBBlk;       // [kb]
 constexpr uint32_t kStageBytes = 2 * kStageA + 2 * kStageB;   // hi + lo of both operands = 48 KB
@@ -56,9 +56,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ float tf32_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
 __device__ __forceinline__ float4 tf32_hi(float4 x) {
-    return make_float4(__uint_as_float(__float_as_uint(x.x) & 0xffffe000u), __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
-                       __uint_as_float(__float_as_uint(x.z) & 0xffffe000u), __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
+    return make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
 }
 __device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
@@ -117,8 +121,9 @@ __global__ void __launch_bounds__(kMmaThreads, 2) blend_forward_mma_kernel(
     // ---- staging roles.  lane -> (qq = lane >> 3: one of 4 adjacent 16-byte pieces, e8 = lane & 7: entry of the K
     // block): 8 lanes fill one 128-byte core matrix, a warp 512 contiguous bytes; per row 64 contiguous global bytes.
     const int qq = lane >> 3, e8 = lane & 7;
-    float4 wreg[4], freg[2];
-    auto load_batch = [&](int b) {
+    // raw operands of the next TWO batches live in two explicit register sets (global latency >> one batch of MMAs)
+    float4 wregA[4], fregA[2], wregB[4], fregB[2];
+    auto load_batch = [&](int b, float4 (&wreg)[4], float4 (&freg)[2]) {
         const WChunk* ck = chunk_ptr(b);
         const int left = (int)n - b * kBatch;  // entries of this batch that exist
 #pragma unroll
@@ -139,7 +144,20 @@ __global__ void __launch_bounds__(kMmaThreads, 2) blend_forward_mma_kernel(
             }
         }
     };
-    auto store_batch = [&](int st) {
+    // K-major no-swizzle operand block (validated by tools/tc_probe.cu; the MN-major forms produced no output there):
+    // element (row r of the 128-row block, entry k of the 8-entry K block) at
+    //     (r / 8) * 256 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4      -> descriptor LBO = 128 B, SBO = 256 B.
+    // A thread holds 4 consecutive rows of ONE entry (a 16-byte piece of a weight / feature row), i.e. 4 scalar stores.
+    auto put4 = [&](unsigned char* blk, int r0, float4 v) {
+        const uint32_t col = (uint32_t)(e8 >> 2) * 128u + (uint32_t)(e8 & 3) * 4u;
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = r0 + j;
+            *reinterpret_cast<float*>(blk + (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u + col) = x[j];
+        }
+    };
+    auto store_batch = [&](int st, float4 (&wreg)[4], float4 (&freg)[2]) {
         unsigned char* base = smem_raw + (size_t)st * kStageBytes;
         unsigned char* a_hi = base;
         unsigned char* a_lo = base + kStageA;
@@ -149,30 +167,27 @@ __global__ void __launch_bounds__(kMmaThreads, 2) blend_forward_mma_kernel(
         for (int it = 0; it < 4; it++) {
             const int c = it * 8 + warp, kb = c >> 4, qblk = c & 15;
             const int q = qblk * 4 + qq, mh = q >> 5, ql = q & 31;
-            const uint32_t off = (uint32_t)(kb * 2 + mh) * kABlk + (uint32_t)ql * 128u + (uint32_t)e8 * 16u;
+            const uint32_t blk = (uint32_t)(kb * 2 + mh) * kABlk;
             const float4 hi = tf32_hi(wreg[it]);
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = tf32_hi(sub4(wreg[it], hi));
+            put4(a_hi + blk, ql * 4, hi);
+            put4(a_lo + blk, ql * 4, tf32_hi(sub4(wreg[it], hi)));
         }
 #pragma unroll
         for (int it = 0; it < 2; it++) {
             const int q = warp * 4 + qq;
-            const uint32_t off = (uint32_t)it * kBBlk + (uint32_t)q * 128u + (uint32_t)e8 * 16u;
             const float4 hi = tf32_hi(freg[it]);
-            *reinterpret_cast<float4*>(b_hi + off) = hi;
-            *reinterpret_cast<float4*>(b_lo + off) = tf32_hi(sub4(freg[it], hi));
+            put4(b_hi + (uint32_t)it * kBBlk, q * 4, hi);
+            put4(b_lo + (uint32_t)it * kBBlk, q * 4, tf32_hi(sub4(freg[it], hi)));
         }
     };
-    // instruction descriptor: D f32 | A, B tf32 | A, B MN-major | N >> 3 | M >> 4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kNch >> 3) << 17) |
-                           ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor: D f32 | A, B tf32 | A, B K-major | N >> 3 | M >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNch >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-    load_batch(0);
-    for (int b = 0; b < nb; b++) {
+    auto step = [&](int b, float4 (&wreg)[4], float4 (&freg)[2]) {
         const int st = b % kStages;
         if (b >= kStages) mbar_wait(&empty_bar[st], (uint32_t)(((b / kStages) - 1) & 1));  // MMAs of batch b-2 retired
-        store_batch(st);
-        if (b + 1 < nb) load_batch(b + 1);  // lands while the tensor core works on this batch
+        store_batch(st, wreg, freg);
+        if (b + 2 < nb) load_batch(b + 2, wreg, freg);  // lands while the tensor core works on this batch and the next
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -181,10 +196,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) blend_forward_mma_kernel(
             const int nkb = ((int)n - b * kBatch > 8) ? 2 : 1;  // a batch whose second K block is empty skips it
             for (int kb = 0; kb < nkb; kb++) {
                 const uint32_t bh = sbase + 2 * kStageA + kb * kBBlk, bl = bh + kStageB;
-                const uint64_t dbh = umma_desc(bh, kBBlk, 128), dbl = umma_desc(bl, kBBlk, 128);
+                const uint64_t dbh = umma_desc(bh, 128, 256), dbl = umma_desc(bl, 128, 256);
                 for (int mh = 0; mh < 2; mh++) {
                     const uint32_t ah = sbase + (uint32_t)(kb * 2 + mh) * kABlk, al = ah + kStageA;
-                    const uint64_t dah = umma_desc(ah, kABlk, 128), dal = umma_desc(al, kABlk, 128);
+                    const uint64_t dah = umma_desc(ah, 128, 256), dal = umma_desc(al, 128, 256);
                     const uint32_t d = tmem + (uint32_t)mh * kNch;
                     const uint32_t first = (b == 0 && kb == 0) ? 0u : 1u;
                     umma_tf32(d, dal, dbh, idesc, first);  // small terms first
@@ -194,6 +209,12 @@ __global__ void __launch_bounds__(kMmaThreads, 2) blend_forward_mma_kernel(
             }
             umma_commit(b + 1 < nb ? &empty_bar[st] : &done_bar);
         }
+    };
+    load_batch(0, wregA, fregA);
+    if (nb > 1) load_batch(1, wregB, fregB);
+    for (int b = 0; b < nb; b += 2) {
+        step(b, wregA, fregA);
+        if (b + 1 < nb) step(b + 1, wregB, fregB);
     }
     mbar_wait(&done_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

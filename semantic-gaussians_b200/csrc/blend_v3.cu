@@ -958,10 +958,13 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
 //     4 x LDG.128 per lane (lane = entry) one slab ahead in registers, stored transposed [ch][entry];
 //   * S is parked in the warp's dL slab region (XOR-swizzled 16-byte chunks: conflict-free both ways) and lane = pixel
 //     runs the reference's back-to-front chain (backward.cu:477-550, dot-product form) over the 32 entries.
-// Shared memory 10.4 KB per warp, 2 CTAs/SM; the warps of a tile share their feature rows through L1/L2 only.
+// Shared memory 7.8 KB per warp, 128 registers, 2 CTAs/SM (a 80-register / 3-CTA build measured 13 % SLOWER on K3:
+// 5.22 vs 4.62 ms — the extra warps thrash the 28 KB of L1 that three CTAs leave for the gathered rows); the warps of
+// a tile share their feature rows through L1/L2 only.
 struct __align__(16) ChainWarpSmem {
     float DS[2][16][32];   // dL/dout slabs [buf][ch][px of the strip]; S[32 entries][32 px] aliases it after the s-pass
-    float FT[2][16][36];   // feature slabs [buf][ch][entry]
+    float FT[16][36];      // feature slab [ch][entry] (single buffer: the same warp stores it between two math blocks);
+                           // during the chain phase: 18 rows x 32 floats of partial gradient terms
     float4 RecA[32], RecB[32];
     const float* Wrow[32];
     uint32_t Gid[32];
@@ -1024,24 +1027,27 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     const int nslab = (C + CK - 1) / CK;
     float (*S)[32] = reinterpret_cast<float (*)[32]>(&ws.DS[0][0][0]);
 
-    // dL slab [CK ch][32 px of this strip]: 4 x cp.async(16 B) per lane
+    // dL slab [CK ch][32 px of this strip]: 4 x cp.async(16 B) per lane; lane -> (channel row (lane >> 3) + 4 i of the
+    // slab, 16-byte piece lane & 7: tile row pc >> 2 of the strip, columns (pc & 3) * 4 ..)
+    const int d_pc = lane & 7;
+    const uint32_t d_y = pix_min.y + 2 * warp + (d_pc >> 2), d_x = pix_min.x + (d_pc & 3) * 4;
+    const bool d_rowin = d_y < (uint32_t)H;
+    const bool d_vec_ok = d_rowin && d_x + 4 <= (uint32_t)W;
+    const float* d_src0 = dL_dpixels + (size_t)(lane >> 3) * plane + (size_t)W * d_y + d_x;
     auto dissue = [&](int sl, int buf) {
+        const float* srcs = d_src0 + (size_t)sl * CK * plane;
 #pragma unroll
         for (int i = 0; i < CK / 4; i++) {
             const int chl = (lane >> 3) + 4 * i;
-            const int ch = sl * CK + chl;
-            const int pc = lane & 7;  // 16-byte piece: tile row pc>>2 of the strip, columns (pc&3)*4..
-            const uint32_t y = pix_min.y + 2 * warp + (pc >> 2);
-            const uint32_t x = pix_min.x + (pc & 3) * 4;
-            const bool rowin = ch < C && y < (uint32_t)H;
-            const float* src = dL_dpixels + (size_t)ch * plane + (size_t)W * y + x;
+            const bool chin = sl * CK + chl < C;
+            const float* src = srcs + (size_t)(4 * i) * plane;
             if (rows16) {
-                const bool ok = rowin && x + 4 <= (uint32_t)W;
-                cp_async16(&ws.DS[buf][chl][pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
+                const bool ok = chin && d_vec_ok;
+                cp_async16(&ws.DS[buf][chl][d_pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
             } else {  // image rows not 16-byte aligned: plain loads, ordered by the warp barrier of the slab loop
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    ws.DS[buf][chl][pc * 4 + u] = (rowin && x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
+                    ws.DS[buf][chl][d_pc * 4 + u] = (chin && d_rowin && d_x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
             }
         }
         cp_async_commit();
@@ -1103,29 +1109,29 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
                 }
             }
         };
-        auto fstore = [&](int buf) {  // lane = entry: conflict-free for every channel row
+        auto fstore = [&]() {  // lane = entry: conflict-free for every channel row
 #pragma unroll
             for (int q = 0; q < CK / 4; q++) {
-                ws.FT[buf][q * 4 + 0][lane] = fpre[q].x;
-                ws.FT[buf][q * 4 + 1][lane] = fpre[q].y;
-                ws.FT[buf][q * 4 + 2][lane] = fpre[q].z;
-                ws.FT[buf][q * 4 + 3][lane] = fpre[q].w;
+                ws.FT[q * 4 + 0][lane] = fpre[q].x;
+                ws.FT[q * 4 + 1][lane] = fpre[q].y;
+                ws.FT[q * 4 + 2][lane] = fpre[q].z;
+                ws.FT[q * 4 + 3][lane] = fpre[q].w;
             }
         };
         fload(0);
         dissue(0, 0);
-        fstore(0);
+        fstore();
         if (nslab > 1) fload(1);
         for (int sl = 0; sl < nslab; sl++) {
             const int buf = sl & 1;
             if (sl + 1 < nslab) { dissue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
-            __syncwarp();  // FT[buf] stored by every lane, DS[buf] landed
+            __syncwarp();  // FT stored by every lane, DS[buf] landed
 #pragma unroll 8
             for (int k = 0; k < CK; k++) {
                 const float4 d0 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8]);
                 const float4 d1 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8 + 4]);
-                const float4 f0 = *reinterpret_cast<const float4*>(&ws.FT[buf][k][eg * 4]);
+                const float4 f0 = *reinterpret_cast<const float4*>(&ws.FT[k][eg * 4]);
                 const float2 fa = make_float2(f0.x, f0.y), fb = make_float2(f0.z, f0.w);
                 const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -1135,9 +1141,9 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
                     acc[i][1] = ffma2(fb, d2, acc[i][1]);
                 }
             }
-            __syncwarp();  // every lane is done with DS[buf] / FT[buf]
+            __syncwarp();  // every lane is done with DS[buf] / FT
             if (sl + 1 < nslab) {
-                fstore(buf ^ 1);
+                fstore();
                 if (sl + 2 < nslab) fload(sl + 2);
             }
         }
@@ -1156,10 +1162,10 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
         // ---- back-to-front chain over the segment (backward.cu:477-550 in dot-product form); slot 0 is the
         // furthest-back entry.  The own-pixel weights are prefetched two entries ahead.  The six per-Gaussian sums
         // over the strip's 32 pixels go through shared memory instead of a shuffle butterfly (ncu: the butterfly was
-        // 62 of ~190 instructions per entry): every lane parks its six terms of up to 5 entries as rows of the (idle)
+        // 62 of ~190 instructions per entry): every lane parks its six terms of up to 3 entries as rows of the (idle)
         // feature-slab buffer, then lane r adds up row r with 8 x LDS.128 and issues that row's one red.global.
-        constexpr int RP = 36, RG = 5;  // row pitch (floats), entries per flush: 30 rows x 144 B <= sizeof(FT)
-        float* RB = &ws.FT[0][0][0];
+        constexpr int RG = 3;  // entries per flush: 18 rows x 128 B = sizeof(FT); 16-byte chunk c of row r sits at c ^ (r & 7)
+        float* RB = &ws.FT[0][0];
         int nbuf = 0;
         float wn0 = __ldg(ws.Wrow[0] + woff);
         float wn1 = cnt > 1 ? __ldg(ws.Wrow[1] + woff) : 0.f;
@@ -1195,16 +1201,19 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
                 gv[5] = G * dL_dalpha;
             }
 #pragma unroll
-            for (int v = 0; v < 6; v++) RB[(nbuf * 6 + v) * RP + lane] = gv[v];
+            for (int v = 0; v < 6; v++) {
+                const int r = nbuf * 6 + v;
+                RB[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))] = gv[v];
+            }
             nbuf++;
             if (nbuf == RG || li == cnt - 1) {
                 __syncwarp();
                 if (lane < nbuf * 6) {
-                    const float4* row = reinterpret_cast<const float4*>(RB + lane * RP);
-                    float4 t = row[0];
+                    const float4* row = reinterpret_cast<const float4*>(RB + lane * 32);
+                    float4 t = row[lane & 7];  // chunk 0 of row `lane`
 #pragma unroll
                     for (int q = 1; q < 8; q++) {
-                        const float4 u = row[q];
+                        const float4 u = row[q ^ (lane & 7)];
                         t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
                     }
                     const float tot = (t.x + t.y) + (t.z + t.w);
@@ -1220,6 +1229,209 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
             }
         }
         __syncwarp();  // the next segment's gather / dL slab overwrite Gid, Wrow, Rec and S
+    }
+}
+
+// ------------------------------------------------------------------------------------ warp-autonomous forward
+// Forward counterpart of chain_backward_warp_kernel (round 2).  The TMA-ring kernel above multiplies every entry of the
+// TILE list into every strip (ncu r01: 57 % FMA pipe, 13 % of the stalls on the per-CTA prologue, 35 % of the FMAs on
+// zero weights).  Here a warp owns (strip, 32-channel slice): it compacts the tile list to the entries whose
+// strip-mask bit is set, streams for each of them 128 B of weights (its strip only — the ring staged the whole 1 KB
+// row for every 64-channel slice) and 128 B of features through a private cp.async double buffer (8 entries per
+// stage) and accumulates an 8 px x 4 ch register tile per lane (16 packed FMAs per 3 LDS.128).  No CTA barrier after
+// the prologue; 64 registers, 4.4 KB of shared memory per warp.  CTA = (tile, SL consecutive slices handled one after
+// the other by every warp).  Accumulation order = list order, like forward.cu:355-356.
+struct __align__(16) FwdWarpSmem {
+    float Wst[2][8][32];   // [stage][entry][pixel of the strip]
+    float Fst[2][8][32];   // [stage][entry][channel of the slice]
+    const float* Wrow[32]; // queue of gathered entries: weight rows (already offset to this strip)
+    uint32_t Gid[32];
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 3) blend_forward_warp_kernel(
+    int W, int H, int C, int SL, const float* __restrict__ features, const float* __restrict__ bg_color,
+    const float* __restrict__ final_T, PoolView pool, float* __restrict__ out_color) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint2 MetaS[kMetaCap];
+    __shared__ uint32_t Cdir[kMetaCap / kChunkEntries];
+
+    const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
+    const int nslices = (C + 31) / 32;
+    const int groups = (nslices + SL - 1) / SL;   // CTAs per tile
+    const int tile = blockIdx.x / groups;
+    const int slice0 = (blockIdx.x % groups) * SL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cg = lane & 7;
+    FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[warp];
+    const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
+    const uint32_t n = pool.count[tile];
+    const uint32_t dbase = pool.dirbase[tile];
+    const size_t plane = (size_t)H * W;
+
+    const uint32_t ncache = min(n, (uint32_t)kMetaCap);
+    for (uint32_t k = tid; k * kChunkEntries < ncache; k += kThreads) Cdir[k] = chunk_of(pool, dbase, (int)k);
+    __syncthreads();
+    for (uint32_t e = tid; e < ncache; e += kThreads)
+        MetaS[e] = __ldg(&pool.chunks[Cdir[e / kChunkEntries]].meta[e & (kChunkEntries - 1)]);
+    __syncthreads();
+    auto chunk_ptr = [&](uint32_t e) -> const WChunk* {
+        return pool.chunks + (e < ncache ? Cdir[e / kChunkEntries] : chunk_of(pool, dbase, (int)(e / kChunkEntries)));
+    };
+    auto meta_of = [&](uint32_t e) -> uint2 {
+        return e < ncache ? MetaS[e] : __ldg(&chunk_ptr(e)->meta[e & (kChunkEntries - 1)]);
+    };
+
+    // output pixels of this lane: 8 consecutive pixels of tile row 2*warp + (pg >> 1), columns (pg & 1) * 8 ..
+    const uint32_t row = pix_min.y + 2 * warp + (pg >> 1);
+    const uint32_t col0 = pix_min.x + (pg & 1) * 8;
+    float Tv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        Tv[i] = (row < (uint32_t)H && col0 + i < (uint32_t)W) ? final_T[(size_t)W * row + col0 + i] : 0.f;
+    const int sp = lane & 7, se = lane >> 3;  // staging role: 16-byte piece sp of entries se and se + 4 of a stage
+
+    for (int sli = 0; sli < SL && slice0 + sli < nslices; sli++) {
+        const int ch0 = (slice0 + sli) * 32;
+        const int nch = min(32, C - ch0);
+        float2 acc[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+
+        uint32_t cursor = 0;  // tile-list entries [cursor, n) are still to be visited (front to back)
+        while (cursor < n) {
+            // ---- gather the next <= 32 entries of this strip
+            int cnt = 0;
+            while (cnt < 32 && cursor < n) {
+                const uint32_t e = cursor + (uint32_t)lane;
+                const bool valid = e < n;
+                const uint2 mt = valid ? meta_of(e) : make_uint2(0u, 0u);
+                const bool bit = valid && ((mt.y >> warp) & 1u);
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                const int room = 32 - cnt;
+                const int nset = __popc(bal);
+                const int rank = __popc(bal & ((1u << lane) - 1u));
+                if (bit && rank < room) {
+                    const int slot = cnt + rank;
+                    ws.Wrow[slot] = &chunk_ptr(e)->w[e & (kChunkEntries - 1)][warp * 32];
+                    ws.Gid[slot] = mt.x;
+                }
+                if (nset <= room) {
+                    cursor += min(32u, n - cursor);
+                    cnt += nset;
+                } else {
+                    const int last_lane = __ffs(__ballot_sync(0xffffffffu, bit && rank == room - 1)) - 1;
+                    cursor += (uint32_t)(last_lane + 1);
+                    cnt = 32;
+                }
+            }
+            __syncwarp();
+            if (cnt == 0) break;
+            const int nst = (cnt + 7) >> 3;
+            auto issue = [&](int st) {  // stage st of the queue -> buffer st & 1 (missing entries / channels: zeros)
+                const int buf = st & 1;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int el = se + 4 * h, q = st * 8 + el;
+                    const bool ok = q < cnt;
+                    const float* wsrc = ok ? ws.Wrow[q] + sp * 4 : pool.chunks->w[0];
+                    cp_async16(&ws.Wst[buf][el][sp * 4], wsrc, ok ? 16 : 0);
+                    if (VEC) {
+                        const bool fok = ok && sp * 4 < nch;
+                        const float* fsrc = fok ? features + (size_t)ws.Gid[q] * C + ch0 + sp * 4 : features;
+                        cp_async16(&ws.Fst[buf][el][sp * 4], fsrc, fok ? 16 : 0);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int c = sp * 4 + u;
+                            ws.Fst[buf][el][c] = (ok && c < nch) ? __ldg(features + (size_t)ws.Gid[q] * C + ch0 + c) : 0.f;
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            issue(0);
+            for (int st = 0; st < nst; st++) {
+                const int buf = st & 1;
+                if (st + 1 < nst) { issue(st + 1); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&ws.Wst[buf][e][pg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&ws.Wst[buf][e][pg * 8 + 4]);
+                    const float4 f0 = *reinterpret_cast<const float4*>(&ws.Fst[buf][e][cg * 4]);
+                    const float2 fa = make_float2(f0.x, f0.y), fb = make_float2(f0.z, f0.w);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float2 w2 = make_float2(wv[i], wv[i]);
+                        acc[i][0] = ffma2(fa, w2, acc[i][0]);
+                        acc[i][1] = ffma2(fb, w2, acc[i][1]);
+                    }
+                }
+                __syncwarp();  // buffer `buf` may be refilled
+            }
+        }
+
+        // ---- non-finite features (see acc_nonfinite above): a warp that sees a non-finite accumulator recomputes its
+        // 32 px x 32 ch with the guarded loop (accumulate only where the weight is non-zero)
+        {
+            float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                z = ffma2(acc[i][0], make_float2(0.f, 0.f), z);
+                z = ffma2(acc[i][1], make_float2(0.f, 0.f), z);
+            }
+            const float t = z.x + z.y;
+            if (__any_sync(0xffffffffu, t != t)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+                for (uint32_t e = 0; e < n; e++) {
+                    const uint2 mt = meta_of(e);
+                    if (!((mt.y >> warp) & 1u)) continue;
+                    const float* wr = &chunk_ptr(e)->w[e & (kChunkEntries - 1)][warp * 32 + pg * 8];
+                    const float* fr = features + (size_t)mt.x * C + ch0 + cg * 4;
+                    float f[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) f[k] = (cg * 4 + k < nch) ? __ldg(fr + k) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float w = wr[i];
+                        if (w != 0.f) {
+                            acc[i][0].x = fmaf(f[0], w, acc[i][0].x);
+                            acc[i][0].y = fmaf(f[1], w, acc[i][0].y);
+                            acc[i][1].x = fmaf(f[2], w, acc[i][1].x);
+                            acc[i][1].y = fmaf(f[3], w, acc[i][1].y);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- out = acc + T * bg (forward.cu:372-373)
+        if (row < (uint32_t)H) {
+            const bool vec = ((W & 3) == 0) && (col0 + 8 <= (uint32_t)W);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int chl = cg * 4 + k;
+                if (chl >= nch) continue;
+                const float bgc = bg_color[ch0 + chl];
+                float* dst = out_color + (size_t)(ch0 + chl) * plane + (size_t)W * row + col0;
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = ((k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x) + Tv[i] * bgc;
+                if (vec) {
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (col0 + i < (uint32_t)W) dst[i] = o[i];
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1315,8 +1527,25 @@ static int launch_forward_gemm(sgb_ctx* ctx, const sgb_view_inputs& in, ImgView 
     const int chunks = (in.C + 63) / 64;
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
     if (vec && blend_mma_enabled()) return launch_forward_mma(ctx, in, im, colors, out_color, pv, s);  // opt-in experiment
+    // SGB_FWD_WARP=1 selects the warp-autonomous kernel (per-strip compacted lists; measured SLOWER than the TMA ring on
+    // K3: 2.98 vs 2.56 ms — kept for A/B measurements and for scenes with sparser strips)
+    static const bool use_warp = [] { const char* e = getenv("SGB_FWD_WARP"); return e && e[0] == '1'; }();
     StageTimer t(ctx, ST_BLEND_FWD, s);
     ctx->launches += 1;
+    if (use_warp) {
+        const int nslices = (in.C + 31) / 32;
+        const int SL = nslices >= 4 ? 4 : nslices;  // 128 channels per CTA: prologue amortised, CTAs still short
+        const int groups = (nslices + SL - 1) / SL;
+        const size_t smem_w = sizeof(FwdWarpSmem) * (kThreads / 32);
+        if (vec)
+            blend_forward_warp_kernel<true><<<tiles * groups, kThreads, smem_w, s>>>(in.W, in.H, in.C, SL, colors, in.background,
+                                                                                    im.final_T, pv, out_color);
+        else
+            blend_forward_warp_kernel<false><<<tiles * groups, kThreads, smem_w, s>>>(in.W, in.H, in.C, SL, colors, in.background,
+                                                                                     im.final_T, pv, out_color);
+        SGB_LAUNCH_CHECK("blend_forward_warp_kernel", in.debug, s);
+        return SGB_OK;
+    }
     if (vec) {
         constexpr int NS = 5;
         const size_t smem_f = (size_t)NS * kChunkEntries * (SGB_TILE_PIX + 64) * sizeof(float);

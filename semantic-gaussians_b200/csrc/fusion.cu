@@ -145,9 +145,13 @@ __global__ void fusion_scatter_kernel(int P, const int* __restrict__ pix_of, uin
 __device__ __forceinline__ float to_f32(__half h) { return __half2float(h); }
 __device__ __forceinline__ float to_f32(float f) { return f; }
 
-// feat_sum[g, :] += map[:, pix(g)] for the visible Gaussians, in pixel order.  Warp = 32 consecutive entries of the
-// pixel-sorted list; CHP channels per pass through a private shared-memory tile [32][CHP] (odd word pitch: the
-// per-lane row writes of the load phase and the per-row reads of the accumulate phase are both conflict-free).
+// feat_sum[g, :] += map[:, pix(g)] for the visible Gaussians, in pixel order.  Work item of a warp = (32 consecutive
+// entries of the pixel-sorted list, one pass of CHP channels); items are handed out grid-stride with the pass index
+// fastest, so a view with few visible Gaussians still spreads over many warps (a first version walked all passes of a
+// batch in one warp: ~0.3 ms of serial latency per view however few Gaussians were visible).  Per item: load phase
+// (lane = Gaussian, one element per channel plane, 16 loads in flight) into a private shared-memory tile [32][CHP]
+// (odd word pitch: the per-lane row writes and the per-row reads are both conflict-free), then the accumulate phase
+// adds 8 rows at a time to the fp32 sums, lanes along the channels (128-byte pieces, 32 loads in flight).
 template <typename T, int CHP>
 __global__ void __launch_bounds__(256) fusion_gather_sorted_kernel(const int* __restrict__ n_visible, int C, int npix,
                                                                    const uint32_t* __restrict__ sorted_ids,
@@ -155,39 +159,53 @@ __global__ void __launch_bounds__(256) fusion_gather_sorted_kernel(const int* __
                                                                    const T* __restrict__ fm,
                                                                    float* __restrict__ feat_sum) {
     constexpr int PITCH = CHP + (sizeof(T) == 2 ? 2 : 1);  // elements; 65 32-bit words either way
+    constexpr int KP = CHP / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * PITCH;
     const int nvis = *n_visible;
+    const int npass = (C + CHP - 1) / CHP;
+    const long long items = (long long)((nvis + 31) / 32) * npass;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b * 32 < nvis; b += warps_total) {
+    for (long long it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += warps_total) {
+        const int b = (int)(it / npass), c0 = (int)(it % npass) * CHP;
+        const int nc = min(CHP, C - c0);
         const int j = b * 32 + lane;
         const bool valid = j < nvis;
         const uint32_t gid = valid ? sorted_ids[j] : 0u;
         uint32_t pix = valid ? sorted_pix[j] : 0u;
-        pix = valid ? pix : __shfl_sync(0xffffffffu, pix, 0);  // idle lanes re-read lane 0's pixel (in range, cached)
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        const T* src = fm + pix;
-        for (int c0 = 0; c0 < C; c0 += CHP) {
-            const int nc = min(CHP, C - c0);
-            // load phase: lane = Gaussian, one element per channel plane
-#pragma unroll 8
-            for (int c = 0; c < CHP; c++)
-                if (c < nc) tile[lane * PITCH + c] = src[(size_t)(c0 + c) * npix];
-            __syncwarp();
-            // accumulate phase: row by row, lanes along the channels (128-byte pieces of the fp32 row)
-            for (int g = 0; g < 32; g++) {
-                if (!((vmask >> g) & 1u)) break;  // valid lanes are a prefix
-                const uint32_t gg = __shfl_sync(0xffffffffu, gid, g);
-                float* dst = feat_sum + (size_t)gg * C + c0;
+        const uint32_t pix0 = __shfl_sync(0xffffffffu, pix, 0);  // executed by every lane (lane 0 is always valid)
+        pix = valid ? pix : pix0;                                // idle lanes re-read lane 0's pixel (in range, cached)
+        const int nrows = min(32, nvis - b * 32);
+        const T* src = fm + (size_t)c0 * npix + pix;
+        // load phase
+#pragma unroll 16
+        for (int c = 0; c < CHP; c++)
+            if (c < nc) tile[lane * PITCH + c] = src[(size_t)c * npix];
+        __syncwarp();
+        // accumulate phase
+        for (int g0 = 0; g0 < nrows; g0 += 8) {
+            float v[8][KP];
+            float* dst[8];
 #pragma unroll
-                for (int k = 0; k < CHP / 32; k++) {
+            for (int u = 0; u < 8; u++) {
+                const uint32_t gg = __shfl_sync(0xffffffffu, gid, (g0 + u) & 31);
+                dst[u] = feat_sum + (size_t)gg * C + c0;
+#pragma unroll
+                for (int k = 0; k < KP; k++) {
                     const int c = lane + 32 * k;
-                    if (c < nc) dst[c] += to_f32(tile[g * PITCH + c]);
+                    v[u][k] = (g0 + u < nrows && c < nc) ? dst[u][c] : 0.f;
                 }
             }
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < KP; k++) {
+                    const int c = lane + 32 * k;
+                    if (g0 + u < nrows && c < nc) dst[u][c] = v[u][k] + to_f32(tile[(g0 + u) * PITCH + c]);
+                }
         }
+        __syncwarp();
     }
 }
 
@@ -301,7 +319,7 @@ extern "C" int sgb_fusion_accumulate(sgb_ctx* ctx, const sgb_fusion_view* v, con
     }
     {
         StageTimer t(ctx, ST_FUSION_GATHER, s);
-        const int gblocks = 148 * 3;
+        const int gblocks = 148 * 3;  // 3 CTAs/SM by shared memory (66 KB each); items are handed out grid-stride
         if (feat_dtype == SGB_FEAT_F16) {
             constexpr int CHP = 128;
             const size_t smem = 8 * 32 * (CHP + 2) * sizeof(__half);
