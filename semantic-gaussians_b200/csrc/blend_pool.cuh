@@ -43,5 +43,10 @@ __device__ __forceinline__ uint32_t chunk_of(const PoolView& pool, uint32_t dbas
 bool blend_mma_enabled();
 int launch_forward_mma(sgb_ctx* ctx, const sgb_view_inputs& in, ImgView im, const float* colors, float* out_color,
                        const PoolView& pv, cudaStream_t s);
+int launch_chain_mma(sgb_ctx* ctx, const sgb_view_inputs& in, GeomView g, ImgView im, const float* colors,
+                     const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, const PoolView& pv,
+                     cudaStream_t s);
+int launch_dfeature_mma(sgb_ctx* ctx, const sgb_view_inputs& in, const float* dL_dpix, float* dL_dcolors,
+                        const PoolView& pv, cudaStream_t s);
 
 }  // namespace sgb

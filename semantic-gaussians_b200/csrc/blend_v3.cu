@@ -1658,6 +1658,8 @@ int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t 
     PoolView pv;
     int rc = pool_for_backward(ctx, in, R, g, b, im, &pv, s);
     if (rc) return rc;
+    if (blend_mma_enabled() && in.C % 4 == 0 && (reinterpret_cast<uintptr_t>(dL_dcolors) & 15) == 0)
+        return launch_dfeature_mma(ctx, in, dL_dpix, dL_dcolors, pv, s);  // opt-in experiment
     const int tiles = num_tiles(in);
     const int chunks = (in.C + 63) / 64;
     const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
@@ -1679,6 +1681,8 @@ int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, 
     if (rc) return rc;
     const int tiles = num_tiles(in);
     const bool vec = (in.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors) & 15) == 0);
+    if (vec && blend_mma_enabled())   // opt-in experiment
+        return launch_chain_mma(ctx, in, g, im, colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, pv, s);
     // SGB_CHAIN_V3=1 selects the first-generation CTA-synchronous kernel (kept for A/B measurements)
     static const bool use_v3 = [] { const char* e = getenv("SGB_CHAIN_V3"); return e && e[0] == '1'; }();
     const size_t smem_g = sizeof(float) * (8 * kSeg * 32 + 2 * 16 * (kSeg + 4) + 8 * 2 * 16 * 32);
