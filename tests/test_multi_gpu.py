@@ -207,7 +207,9 @@ def test_batched_view_shards_with_overlapped_exchange_match_single_gpu():
     single = [t.cpu().numpy() for t in _batch_grads(torch.device("cuda:0"), [0, 1, 2, 3])]
     for a, b, s in zip(res[0][1], res[1][1], single):
         assert np.array_equal(a, b)
-        assert np.abs(a - s).max() <= 1e-5 * np.abs(s).max() + 1e-9
+        # both sides sum per-tile partial gradients with red.global in scheduling order (two runs of the same view
+        # already differ by ~1e-5 of the scale); the cross-rank sum adds fp32 re-association
+        assert np.abs(a - s).max() <= 1e-4 * np.abs(s).max() + 1e-9
 
 
 def _fusion_partial(dev, view_ids):

@@ -11,9 +11,9 @@ P, C, w, h, nviews = 2_000_000, 512, 640, 480, 6
 scene = make_scene(P, 0, kind="room"); cams = room_cameras(nviews, w, h)
 fm = torch.from_numpy(np.random.default_rng(0).standard_normal((C, h, w)).astype(np.float16)).to(dev)
 xyz = torch.as_tensor(scene.xyz, device=dev); fs = torch.zeros((P, C), device=dev); cnt = torch.zeros(P, device=dev)
-depth = torch.full((h, w), 2.5, device=dev)
+depth = None   # the K5 bench rule (`depth: none`, fusion_utils.py:70-72): ~480 k visible Gaussians per view
 ctx = _lib.ctx_for(0, torch.cuda.current_stream(dev).cuda_stream)
-mappers = [PointCloudToImageMapper([w, h], 0.5, 10, c.intrinsics(), device=dev) for c in cams]
+mappers = [PointCloudToImageMapper([w, h], 0.25, 10, c.intrinsics(), device=dev) for c in cams]
 for i in range(nviews): mappers[i].accumulate(cams[i].world_view_transform, xyz, fm, fs, cnt, depth)
 torch.cuda.synchronize(); _lib.profile_enable(ctx, True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True); e0.record()
