@@ -506,12 +506,12 @@ def view_stats(h, cfg, pc, feats_or_none, cam, bg):
     return out
 
 
-def roofline_block(per_stage, ab, candidates, src_hash, note=None):
+def roofline_block(per_stage, ab, candidates, src_hash, note=None, config="K3"):
     peak, peak_src = measured_peaks()
     dom = max(candidates, key=lambda k: per_stage.get(k, 0.0))
     dom_ms = per_stage.get(dom, float("nan"))
     achieved = ab[dom] / (dom_ms * 1e-3) * 1e-9
-    traffic, tsrc = traffic_for(dom, src_hash)
+    traffic, tsrc = traffic_for(f"{config}.{dom}", src_hash)   # captures are per config: K2 and K3 blend different kernels
     r = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
          "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": ab[dom], "kernel_ms": dom_ms,
          "peak_source": peak_src}
@@ -889,7 +889,7 @@ def run_k2(args, rank, world, local_rank):
                    "l2": "8 cycling views; 45 M-instance sort streams (0.5 GB) exceed L2", **stats},
         "views_per_s": value * 1e6, "hbm_gbs_effective": eff, "hbm_frac_effective": eff / peak,
         "stage_ms": per_stage, "kernel_ms_per_step": sum(per_stage.values()),
-        "roofline": roofline_block(per_stage, ab, ("blend_fwd", "tile_sort"), binfo["source_sha256_16"]),
+        "roofline": roofline_block(per_stage, ab, ("blend_fwd", "tile_sort"), binfo["source_sha256_16"], config="K2"),
         "e2e": {"value": views / (ms_e2e * 1e-3) * 1e-6, "unit": "Mviews/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 35 * 4, "d2h_bytes_per_step": 16 * W * H,
                 "api": "render(): camera from pinned host memory, RGB image + median depth copied back to pinned memory"},
@@ -1034,7 +1034,8 @@ def run_k4(args, rank, world, local_rank):
                   "hbm_gbs_effective": batch_bytes / (ms_nc / steps * 1e-3) * 1e-9,
                   "hbm_frac_effective": batch_bytes / (ms_nc / steps * 1e-3) * 1e-9 / peak},
         "roofline": roofline_block(per_stage, ab, ("blend_fwd", "blend_bwd", "dfeature", "alpha_pass"),
-                                   binfo["source_sha256_16"], "C=512 blend: fp32-FMA bound by design; see fma_roofline"),
+                                   binfo["source_sha256_16"], "C=512 blend: fp32-FMA bound by design; see fma_roofline",
+                                   config="K4"),
         "fma_roofline": fma_roofline(C, stats["blended_pairs"], per_stage),
         "batched_vs_loop": {"batched_ms_per_step_no_exchange": ms_nc / steps,
                             "per_view_loop_ms_per_step_no_exchange": ms_loop / nloop,
@@ -1167,7 +1168,10 @@ def run_k5(args, rank, world, local_rank):
         "views_per_s": value * 1e6, "stage_ms": per_stage,
         "bytes": {"per_view_algorithmic": per_view, "final_normalise": 8 * P * C},
         "roofline": {"bound": "hbm", "kernel": "fusion view (project + sort + gather/accumulate kernels)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic_for("K5.fusion_gather", binfo["source_sha256_16"])[0],
+                     "traffic_source": "gather/accumulate kernel alone (the dominant launch of the view), " +
+                                       str(traffic_for("K5.fusion_gather", binfo["source_sha256_16"])[1]),
                      "algorithmic_bytes": per_view, "kernel_ms": kernel_view_ms, "peak_source": peak_src},
         "exchange": {"bytes": 4 * P * C + 4 * P, "ms_per_step_without_exchange_and_normalise": ms_nc / steps,
                      "exposed_ms_per_step": (ms_dev - ms_nc) / steps},
