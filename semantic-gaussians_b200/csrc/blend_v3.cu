@@ -35,6 +35,15 @@ namespace {
 
 constexpr int kThreads = SGB_TILE_PIX;
 
+// Lane -> operand-group mapping of the register-tiled GEMM loops (round 2, measured with tools/lds_probe.cu under ncu
+// on B200): a warp-wide LDS.128 costs 2 shared-memory wavefronts when every aligned group of 4 lanes reads at most 2
+// distinct 16-byte chunks and each half-warp at most 8 (conflict-free) chunks, and 4 wavefronts otherwise.  With the
+// natural split (one operand indexed by lane & 7, the other by lane >> 3) the lane & 7 operand pays 4 per load and the
+// L1 data pipe — not the FMA pipe — bounded all three contraction kernels (ncu r02: 68 / 74 / 83 % of peak).  Giving
+// each operand exactly one of the two low lane bits makes every operand load a 2-wavefront load.
+__device__ __forceinline__ int lane_group8(int lane) { return (lane & 1) | (((lane >> 2) & 3) << 1); }  // bits 0, 2, 3
+__device__ __forceinline__ int lane_group4(int lane) { return ((lane >> 1) & 1) | ((lane >> 4) << 1); } // bits 1, 4
+
 template <int N>
 __device__ __forceinline__ void xreduce_step(float (&v)[8], int lane, int step) {
     const bool upper = (lane & step) != 0;
@@ -433,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
     const int ch0 = (blockIdx.x % nchunksC) * CH;
     const int nch = min(CH, C - ch0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, cg = lane & 7;
+    const int pg = lane_group4(lane), cg = lane_group8(lane);
     const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
 
     const uint32_t n = pool.count[tile];
@@ -625,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     }
     cp_async_commit();
 
-    const int eg = lane >> 3, cg = lane & 7;
+    const int eg = lane_group4(lane), cg = lane_group8(lane);
     for (uint32_t base = 0; base < n; base += 128) {
         const int cnt = (int)min(128u, n - base);
         __syncthreads();  // previous pass done with Wrow / Gid
@@ -958,13 +967,16 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_gemm_kernel(
 //     4 x LDG.128 per lane (lane = entry) one slab ahead in registers, stored transposed [ch][entry];
 //   * S is parked in the warp's dL slab region (XOR-swizzled 16-byte chunks: conflict-free both ways) and lane = pixel
 //     runs the reference's back-to-front chain (backward.cu:477-550, dot-product form) over the 32 entries.
-// Shared memory 7.8 KB per warp, 128 registers, 2 CTAs/SM (a 80-register / 3-CTA build measured 13 % SLOWER on K3:
+// Shared memory 9.3 KB per warp, 128 registers, 2 CTAs/SM (a 80-register / 3-CTA build measured 13 % SLOWER on K3:
 // 5.22 vs 4.62 ms — the extra warps thrash the 28 KB of L1 that three CTAs leave for the gathered rows); the warps of
 // a tile share their feature rows through L1/L2 only.
+constexpr int kChainRG = 5;  // entries whose six gradient terms are summed over the strip per flush (30 of 32 lanes busy)
 struct __align__(16) ChainWarpSmem {
     float DS[2][16][32];   // dL/dout slabs [buf][ch][px of the strip]; S[32 entries][32 px] aliases it after the s-pass
-    float FT[16][36];      // feature slab [ch][entry] (single buffer: the same warp stores it between two math blocks);
-                           // during the chain phase: 18 rows x 32 floats of partial gradient terms
+    union {
+        float FT[2][16][36];           // s-pass: feature slabs [buf][ch][entry]
+        float RB[kChainRG * 6][32];    // chain phase: partial gradient terms, one row per (entry of the group, term)
+    };
     float4 RecA[32], RecB[32];
     const float* Wrow[32];
     uint32_t Gid[32];
@@ -984,7 +996,7 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pg = lane >> 3, eg = lane & 7;
+    const int pg = lane_group4(lane), eg = lane_group8(lane);
     ChainWarpSmem& ws = reinterpret_cast<ChainWarpSmem*>(smem_raw)[warp];
     const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
     const uint32_t tx = tid & (SGB_TILE - 1), ty = tid >> 4;
@@ -1034,22 +1046,40 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     const bool d_rowin = d_y < (uint32_t)H;
     const bool d_vec_ok = d_rowin && d_x + 4 <= (uint32_t)W;
     const float* d_src0 = dL_dpixels + (size_t)(lane >> 3) * plane + (size_t)W * d_y + d_x;
+    // Fast path (16-byte aligned image rows, full slab): the lane keeps a running source pointer; a lane whose piece is
+    // outside the image points at the image base with zero strides and copies 0 bytes (cp.async zero-fills).
+    const char* const d_base = reinterpret_cast<const char*>(d_vec_ok ? d_src0 : dL_dpixels);
+    const size_t d_step4 = d_vec_ok ? 4 * plane * sizeof(float) : 0;       // 4 channel rows further
+    const size_t d_stepslab = d_vec_ok ? CK * plane * sizeof(float) : 0;   // next slab
+    const int d_bytes = d_vec_ok ? 16 : 0;
+    const char* d_run = d_base;
     auto dissue = [&](int sl, int buf) {
-        const float* srcs = d_src0 + (size_t)sl * CK * plane;
+        if (rows16 && (sl + 1) * CK <= C) {
+            float* dst = &ws.DS[buf][lane >> 3][d_pc * 4];
+            const char* src = d_run;
 #pragma unroll
-        for (int i = 0; i < CK / 4; i++) {
-            const int chl = (lane >> 3) + 4 * i;
-            const bool chin = sl * CK + chl < C;
-            const float* src = srcs + (size_t)(4 * i) * plane;
-            if (rows16) {
-                const bool ok = chin && d_vec_ok;
-                cp_async16(&ws.DS[buf][chl][d_pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
-            } else {  // image rows not 16-byte aligned: plain loads, ordered by the warp barrier of the slab loop
+            for (int i = 0; i < CK / 4; i++) {
+                cp_async16(dst + i * 4 * 32, src, d_bytes);
+                src += d_step4;
+            }
+        } else {
+            const float* srcs = d_src0 + (size_t)sl * CK * plane;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    ws.DS[buf][chl][d_pc * 4 + u] = (chin && d_rowin && d_x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
+            for (int i = 0; i < CK / 4; i++) {
+                const int chl = (lane >> 3) + 4 * i;
+                const bool chin = sl * CK + chl < C;
+                const float* src = srcs + (size_t)(4 * i) * plane;
+                if (rows16) {
+                    const bool ok = chin && d_vec_ok;
+                    cp_async16(&ws.DS[buf][chl][d_pc * 4], ok ? src : dL_dpixels, ok ? 16 : 0);
+                } else {  // image rows not 16-byte aligned: plain loads, ordered by the warp barrier of the slab loop
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        ws.DS[buf][chl][d_pc * 4 + u] = (chin && d_rowin && d_x + u < (uint32_t)W) ? __ldg(src + u) : 0.f;
+                }
             }
         }
+        d_run += d_stepslab;
         cp_async_commit();
     };
 
@@ -1091,9 +1121,27 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
         float2 acc[8][2];  // [px][entry pair]
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+        // Feature slab [32 entries][16 ch] -> FT[ch][entry].  Fast path (16-byte aligned rows, full slab): lane
+        // (r8 = lane >> 2, c4 = lane & 3) loads channels 4c4..4c4+3 of entries r8 + 8q, so one LDG.128 covers 8 rows x
+        // 64 contiguous bytes (8 L1 tag lookups; lane = entry touched ~27 lines per instruction and the feature gather
+        // alone was a third of the kernel's L1 wavefronts, ncu r02).  FT rows of channels 8..15 hold their 8-entry
+        // blocks swapped pairwise (block b at b ^ 1) — with the 36-float pitch that makes the transposing stores of
+        // this mapping conflict-free; the s-pass reads entry group eg of channel k at chunk eg ^ ((k >> 3) << 1).
         float4 fpre[CK / 4];
-        const float* frow = features + (size_t)ws.Gid[min(lane, cnt - 1)] * C;
+        const int f_r8 = lane >> 2, f_c4 = lane & 3;
+        const float* frow = features + (size_t)ws.Gid[min(lane, cnt - 1)] * C;          // general path: lane = entry
+        uint32_t f_gid[CK / 4];                                                            // fast path: 4 rows per lane
+#pragma unroll
+        for (int q = 0; q < CK / 4; q++) f_gid[q] = ws.Gid[min(f_r8 + 8 * q, cnt - 1)];    // rows >= cnt: duplicates
+        auto slab_fast = [&](int sl) { return VEC && (sl + 1) * CK <= C; };
         auto fload = [&](int sl) {
+            if (slab_fast(sl)) {
+                const int choff = sl * CK + f_c4 * 4;
+#pragma unroll
+                for (int q = 0; q < CK / 4; q++)
+                    fpre[q] = __ldg(reinterpret_cast<const float4*>(features + (size_t)f_gid[q] * C + choff));
+                return;
+            }
 #pragma unroll
             for (int q = 0; q < CK / 4; q++) {
                 const int chb = sl * CK + q * 4;
@@ -1109,29 +1157,50 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
                 }
             }
         };
-        auto fstore = [&]() {  // lane = entry: conflict-free for every channel row
+        const int f_swap = (f_c4 >> 1) * 8;  // channels 8..15: 8-entry blocks swapped pairwise
+        auto fstore = [&](int buf, int sl) {
+            if (slab_fast(sl)) {
 #pragma unroll
-            for (int q = 0; q < CK / 4; q++) {
-                ws.FT[q * 4 + 0][lane] = fpre[q].x;
-                ws.FT[q * 4 + 1][lane] = fpre[q].y;
-                ws.FT[q * 4 + 2][lane] = fpre[q].z;
-                ws.FT[q * 4 + 3][lane] = fpre[q].w;
+                for (int q = 0; q < CK / 4; q++) {
+                    float* col = &ws.FT[buf][f_c4 * 4][8 * q + f_r8 + ((q & 1) ? -f_swap : f_swap)];
+                    col[0 * 36] = fpre[q].x;
+                    col[1 * 36] = fpre[q].y;
+                    col[2 * 36] = fpre[q].z;
+                    col[3 * 36] = fpre[q].w;
+                }
+                return;
+            }
+#pragma unroll
+            for (int q = 0; q < CK / 4; q++) {  // lane = entry, channels 4q..4q+3
+                const int pos = lane ^ ((q >> 1) << 3);
+                ws.FT[buf][q * 4 + 0][pos] = fpre[q].x;
+                ws.FT[buf][q * 4 + 1][pos] = fpre[q].y;
+                ws.FT[buf][q * 4 + 2][pos] = fpre[q].z;
+                ws.FT[buf][q * 4 + 3][pos] = fpre[q].w;
             }
         };
+        // One warp barrier per slab: at the top of iteration sl every lane has finished the math of slab sl-1, so the
+        // other buffers (dL by cp.async, features from the registers loaded one slab earlier) can be refilled BEFORE
+        // the math of slab sl and their latency hides behind it.
         fload(0);
+        d_run = d_base;
         dissue(0, 0);
-        fstore();
+        fstore(0, 0);
         if (nslab > 1) fload(1);
         for (int sl = 0; sl < nslab; sl++) {
             const int buf = sl & 1;
-            if (sl + 1 < nslab) { dissue(sl + 1, buf ^ 1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            __syncwarp();  // FT stored by every lane, DS[buf] landed
+            cp_async_wait<0>();
+            __syncwarp();  // DS[buf] landed, FT[buf] stored by every lane; DS/FT[buf ^ 1] are free
+            if (sl + 1 < nslab) {
+                dissue(sl + 1, buf ^ 1);
+                fstore(buf ^ 1, sl + 1);
+                if (sl + 2 < nslab) fload(sl + 2);
+            }
 #pragma unroll 8
             for (int k = 0; k < CK; k++) {
                 const float4 d0 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8]);
                 const float4 d1 = *reinterpret_cast<const float4*>(&ws.DS[buf][k][pg * 8 + 4]);
-                const float4 f0 = *reinterpret_cast<const float4*>(&ws.FT[k][eg * 4]);
+                const float4 f0 = *reinterpret_cast<const float4*>(&ws.FT[buf][k][(eg ^ ((k >> 3) << 1)) * 4]);
                 const float2 fa = make_float2(f0.x, f0.y), fb = make_float2(f0.z, f0.w);
                 const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -1141,12 +1210,8 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
                     acc[i][1] = ffma2(fb, d2, acc[i][1]);
                 }
             }
-            __syncwarp();  // every lane is done with DS[buf] / FT
-            if (sl + 1 < nslab) {
-                fstore();
-                if (sl + 2 < nslab) fload(sl + 2);
-            }
         }
+        __syncwarp();  // every lane is done with DS / FT
         // ---- park S[entry][px] in the (now free) dL slab region; 16-byte chunk c of row r sits at chunk c ^ (r >> 2)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -1160,73 +1225,81 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
         __syncwarp();
 
         // ---- back-to-front chain over the segment (backward.cu:477-550 in dot-product form); slot 0 is the
-        // furthest-back entry.  The own-pixel weights are prefetched two entries ahead.  The six per-Gaussian sums
-        // over the strip's 32 pixels go through shared memory instead of a shuffle butterfly (ncu: the butterfly was
-        // 62 of ~190 instructions per entry): every lane parks its six terms of up to 3 entries as rows of the (idle)
-        // feature-slab buffer, then lane r adds up row r with 8 x LDS.128 and issues that row's one red.global.
-        constexpr int RG = 3;  // entries per flush: 18 rows x 128 B = sizeof(FT); 16-byte chunk c of row r sits at c ^ (r & 7)
-        float* RB = &ws.FT[0][0];
-        int nbuf = 0;
-        float wn0 = __ldg(ws.Wrow[0] + woff);
-        float wn1 = cnt > 1 ? __ldg(ws.Wrow[1] + woff) : 0.f;
-        for (int li = 0; li < cnt; li++) {
-            const float w = wn0;
-            wn0 = wn1;
-            if (li + 2 < cnt) wn1 = __ldg(ws.Wrow[li + 2] + woff);
-            const float sdot = S[li][(((lane >> 2) ^ (li >> 2)) << 2) | (lane & 3)];
-            const float4 a = ws.RecA[li], con_o = ws.RecB[li];
-            float gv[6];
+        // furthest-back entry.  Entries go in groups of kChainRG, fully unrolled (every shared-memory address of the
+        // group is a constant plus a lane term — ncu r02: 40 of ~170 instructions per entry were address arithmetic
+        // of the runtime-indexed version); the own-pixel weights of the next group are in flight during the current
+        // one.  The six per-Gaussian sums over the strip's 32 pixels go through shared memory instead of a shuffle
+        // butterfly: every lane parks its terms as rows of RB, then lane r adds up row r with 8 x LDS.128 and issues
+        // that row's one red.global.  16-byte chunk c of row r sits at c ^ (r & 7): conflict-free both ways.
+        // The transmittance in front of an entry is recovered as T_behind + w (w = alpha T_front is what the forward
+        // stored): one add instead of the reference's T / (1 - alpha), same value to an ulp and no error build-up.
+        constexpr int RG = kChainRG;
+        float wc[RG], wn[RG];
 #pragma unroll
-            for (int v = 0; v < 6; v++) gv[v] = 0.f;
-            if (w != 0.f) {
-                const float2 d = {a.x - pixf.x, a.y - pixf.y};
-                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                const float G = exp(power);
-                const float alpha = min(0.99f, con_o.w * G);
-                T = T / (1.f - alpha);
-                A = last_alpha * s_last + (1.f - last_alpha) * A;
-                s_last = sdot;
-                float dL_dalpha = (sdot - A) * T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                const float dL_dG = con_o.w * dL_dalpha;
-                const float gdx = G * d.x, gdy = G * d.y;
-                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
-                gv[1] = dL_dG * dG_ddely * ddely_dy;
-                gv[2] = -0.5f * gdx * d.x * dL_dG;
-                gv[3] = -0.5f * gdx * d.y * dL_dG;
-                gv[4] = -0.5f * gdy * d.y * dL_dG;
-                gv[5] = G * dL_dalpha;
-            }
+        for (int u = 0; u < RG; u++) wc[u] = u < cnt ? __ldg(ws.Wrow[u] + woff) : 0.f;
+        for (int base = 0; base < cnt; base += RG) {
 #pragma unroll
-            for (int v = 0; v < 6; v++) {
-                const int r = nbuf * 6 + v;
-                RB[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))] = gv[v];
-            }
-            nbuf++;
-            if (nbuf == RG || li == cnt - 1) {
-                __syncwarp();
-                if (lane < nbuf * 6) {
-                    const float4* row = reinterpret_cast<const float4*>(RB + lane * 32);
-                    float4 t = row[lane & 7];  // chunk 0 of row `lane`
+            for (int u = 0; u < RG; u++) wn[u] = base + RG + u < cnt ? __ldg(ws.Wrow[base + RG + u] + woff) : 0.f;
 #pragma unroll
-                    for (int q = 1; q < 8; q++) {
-                        const float4 u = row[q ^ (lane & 7)];
-                        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            for (int u = 0; u < RG; u++) {
+                const int li = base + u;
+                if (li < cnt) {  // warp-uniform
+                    // Branch-free per lane (selects instead of `if (w != 0)`): the five entries of a group then sit in
+                    // one basic block and the scheduler overlaps their LDS -> exp -> product latencies.
+                    const float w = wc[u];
+                    const bool on = w != 0.f;
+                    const float sdot = S[li][(((lane >> 2) ^ (li >> 2)) << 2) | (lane & 3)];
+                    const float4 a = ws.RecA[li], con_o = ws.RecB[li];
+                    const float2 d = {a.x - pixf.x, a.y - pixf.y};
+                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    const float G = __expf(power);
+                    const float alpha = fminf(0.99f, con_o.w * G);
+                    T += w;
+                    const float A_new = last_alpha * s_last + (1.f - last_alpha) * A;
+                    A = on ? A_new : A;
+                    s_last = on ? sdot : s_last;
+                    last_alpha = on ? alpha : last_alpha;
+                    float dL_dalpha = (sdot - A) * T;
+                    if (bg_nonzero) dL_dalpha -= T_final / (1.f - alpha) * bgdot;
+                    const float dL_dG = con_o.w * dL_dalpha;
+                    const float gdx = G * d.x, gdy = G * d.y;
+                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                    float gv[6];
+                    gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    gv[1] = dL_dG * dG_ddely * ddely_dy;
+                    gv[2] = -0.5f * gdx * d.x * dL_dG;
+                    gv[3] = -0.5f * gdx * d.y * dL_dG;
+                    gv[4] = -0.5f * gdy * d.y * dL_dG;
+                    gv[5] = G * dL_dalpha;
+#pragma unroll
+                    for (int v = 0; v < 6; v++) {
+                        const int r = u * 6 + v;  // compile-time
+                        ws.RB[r][(((lane >> 2) ^ (r & 7)) << 2) | (lane & 3)] = on ? gv[v] : 0.f;
                     }
-                    const float tot = (t.x + t.y) + (t.z + t.w);
-                    const int slot = lane / 6, comp = lane - slot * 6;
-                    const size_t id = ws.Gid[li - (nbuf - 1) + slot];
-                    float* dst = comp < 2 ? dL_dmean2D + id * 3 + comp
-                               : comp < 5 ? dL_dconic2D + id * 4 + (comp == 4 ? 3 : comp - 2)
-                                          : dL_dopacity + id;
-                    red_add_f32(dst, tot);
                 }
-                __syncwarp();
-                nbuf = 0;
             }
+            __syncwarp();
+            const int nvalid = min(RG, cnt - base);
+            if (lane < nvalid * 6) {
+                const float4* row = reinterpret_cast<const float4*>(&ws.RB[lane][0]);
+                float4 t = row[lane & 7];  // chunk 0 of row `lane`
+#pragma unroll
+                for (int q = 1; q < 8; q++) {
+                    const float4 uu = row[q ^ (lane & 7)];
+                    t.x += uu.x; t.y += uu.y; t.z += uu.z; t.w += uu.w;
+                }
+                const float tot = (t.x + t.y) + (t.z + t.w);
+                const int slot = lane / 6, comp = lane - slot * 6;
+                const size_t id = ws.Gid[base + slot];
+                float* dst = comp < 2 ? dL_dmean2D + id * 3 + comp
+                           : comp < 5 ? dL_dconic2D + id * 4 + (comp == 4 ? 3 : comp - 2)
+                                      : dL_dopacity + id;
+                red_add_f32(dst, tot);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < RG; u++) wc[u] = wn[u];
         }
         __syncwarp();  // the next segment's gather / dL slab overwrite Gid, Wrow, Rec and S
     }
