@@ -26,6 +26,8 @@
 // Results are unchanged: the integer outputs come from the verbatim chain; every accumulator still
 // adds its Gaussians in depth order.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 #include "blend_pool.cuh"
 
@@ -390,6 +392,17 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int 
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// 3-D tensor tile global -> shared through the TMA engine (SASS: UTMALDG): box corner (x, y, z) in elements, out-of-range
+// elements arrive as zeros; completion is signalled on `bar` as the box's bytes.  dst 128-byte aligned.
+__device__ __forceinline__ void tma_tile3d_g2s(void* dst_smem, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+// Orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy (TMA) writes.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -588,17 +601,23 @@ __global__ void __launch_bounds__(kThreads, 2) blend_forward_tma_kernel(
 // CTA = (tile, 64-channel chunk).  The dL tile is copied once into shared memory in its native
 // [channel][pixel] order by cp.async row pieces (no transposing stores); warp w owns entries
 // 16w..16w+15 of each 128-entry pass and streams their weight rows through a private double-buffered
-// slab [16][32 px].  Lane = (eg, cg) accumulates entries {eg + 4j} x channels {cg + 8k} (interleaved so
-// that both operand reads are bank-conflict free); one K step covers 4 pixels with LDS.128 of both
-// operands, and the packed FMAs pair (even, odd) pixels — no register duplication, the two halves are
-// added at the end.
+// slab [16][32 px].  Lane = (eg, cg) accumulates entries {eg + 4j} x channels {4cg..4cg+3} U {32+4cg..32+4cg+3}; one K
+// step covers 4 pixels with LDS.128 of both operands, and the packed FMAs pair (even, odd) pixels — no register
+// duplication, the two halves are added at the end.
+// Round 2 (ncu + tools/lds_probe.cu): the kernel was bound by the LSU, not the FMA pipe — 32 scalar red.global per
+// lane and pass (~30-40 LSU cycles each) on top of 4-wavefront operand loads.  Now
+//   * a lane owns two blocks of 4 CONSECUTIVE channels, so a Gaussian's sums leave as two red.global.add.v4.f32
+//     (8 reductions per lane and pass instead of 32);
+//   * the 16-byte pixel quads of channel row r sit at quad ^ ((r >> 2) & 7): the 8 channel groups of one load then hit 8
+//     different bank groups although their rows are 4 apart (pitch 256 floats, no padding);
+//   * eg / cg come from lane_group4 / lane_group8: every operand load is a 2-wavefront LDS.128.
 template <int CH>
 __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H, int C,
                                                                    const float* __restrict__ dL_dpixels,
                                                                    PoolView pool, float* __restrict__ dL_dcolors) {
     static_assert(CH == 64, "64-channel chunks");
-    constexpr int DP = SGB_TILE_PIX + 4;  // pitch of a channel row of the dL tile
-    constexpr int WP = 36;                // pitch of the per-warp weight slab rows (32 px + pad)
+    constexpr int DP = SGB_TILE_PIX;  // pitch of a channel row of the dL tile (quads XOR-swizzled, see above)
+    constexpr int WP = 36;            // pitch of the per-warp weight slab rows (32 px + pad)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float(*dLs)[DP] = reinterpret_cast<float(*)[DP]>(smem_raw);
     float* wslab = reinterpret_cast<float*>(smem_raw + sizeof(float) * CH * DP);
@@ -617,11 +636,11 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     const uint2 pix_min = {(uint32_t)(tile % tiles_x) * SGB_TILE, (uint32_t)(tile / tiles_x) * SGB_TILE};
     const size_t plane = (size_t)H * W;
     const bool rows16 = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dpixels) & 15) == 0;
-    // dL tile -> smem [ch][px]: 16-byte pieces (4 pixels of one tile row of one channel)
+    // dL tile -> smem [ch][quad ^ swizzle][4 px]: 16-byte pieces (4 pixels of one tile row of one channel)
     for (int idx = tid; idx < CH * SGB_TILE * 4; idx += kThreads) {
         const int pc = idx & 3, r = (idx >> 2) & (SGB_TILE - 1), c = idx >> 6;
         const uint32_t y = pix_min.y + r, x = pix_min.x + pc * 4;
-        float* dst = &dLs[c][r * SGB_TILE + pc * 4];
+        float* dst = &dLs[c][((r * 4 + pc) ^ ((c >> 2) & 7)) * 4];
         const float* src = dL_dpixels + (size_t)(ch0 + c) * plane + (size_t)W * y + x;
         const bool rowok = c < nch && y < (uint32_t)H;
         if (rows16) {
@@ -635,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
     cp_async_commit();
 
     const int eg = lane_group4(lane), cg = lane_group8(lane);
+    const bool red16 = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dcolors) & 15) == 0);
     for (uint32_t base = 0; base < n; base += 128) {
         const int cnt = (int)min(128u, n - base);
         __syncthreads();  // previous pass done with Wrow / Gid
@@ -657,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                     cp_async16(&wsl[buf][(lane >> 3) + 4 * i][(lane & 7) * 4], lrow[i] + sl * 32, 16);
                 cp_async_commit();
             };
-            float2 acc[4][8];  // [entry eg+4j][channel cg+8k], .x even pixels, .y odd pixels
+            float2 acc[4][8];  // [entry eg+4j][channel (k >> 2) * 32 + 4 cg + (k & 3)], .x even pixels, .y odd pixels
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -672,10 +692,12 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
                 // front of its first consumer (ncu: half of all stall samples were short-scoreboard waits on
                 // those FFMA2s).  dL rows are fetched two K-steps ahead, the next pixel quad's weights while
                 // the current quad is being consumed.
-                const float* dbase = &dLs[cg][sl * 32];
+                const float* drow = &dLs[4 * cg][0];
                 const float* wbase = &wsl[buf][eg][0];
-                auto ld_d = [&](int step) {  // step = p4 * 8 + k
-                    return *reinterpret_cast<const float4*>(dbase + (step & 7) * 8 * DP + (step >> 3) * 4);
+                auto ld_d = [&](int step) {  // step = p4 * 8 + k; row (k >> 2) * 32 + 4 cg + (k & 3), quad sl * 8 + p4
+                    const int k = step & 7, p4 = step >> 3;
+                    return *reinterpret_cast<const float4*>(drow + ((k >> 2) * 32 + (k & 3)) * DP +
+                                                            (((sl * 8 + p4) ^ cg) << 2));
                 };
                 float4 wq[4], wn[4];
 #pragma unroll
@@ -712,10 +734,21 @@ __global__ void __launch_bounds__(kThreads, 2) dfeature_gemm_kernel(int W, int H
             for (int j = 0; j < 4; j++) {
                 const int e = warp * 16 + eg + 4 * j;
                 if (e < cnt) {
-                    float* dst = dL_dcolors + (size_t)Gid[e] * C + ch0;
+                    float* dst = dL_dcolors + (size_t)Gid[e] * C + ch0 + 4 * cg;
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        if (cg + 8 * k < nch) red_add_f32(dst + cg + 8 * k, acc[j][k].x + acc[j][k].y);
+                    for (int h = 0; h < 2; h++) {
+                        const int chl = h * 32 + 4 * cg;
+                        const float4 v = make_float4(acc[j][4 * h + 0].x + acc[j][4 * h + 0].y, acc[j][4 * h + 1].x + acc[j][4 * h + 1].y,
+                                                     acc[j][4 * h + 2].x + acc[j][4 * h + 2].y, acc[j][4 * h + 3].x + acc[j][4 * h + 3].y);
+                        if (red16 && chl + 4 <= nch) {
+                            red_add_v4_f32(dst + h * 32, v);
+                        } else {
+                            if (chl + 0 < nch) red_add_f32(dst + h * 32 + 0, v.x);
+                            if (chl + 1 < nch) red_add_f32(dst + h * 32 + 1, v.y);
+                            if (chl + 2 < nch) red_add_f32(dst + h * 32 + 2, v.z);
+                            if (chl + 3 < nch) red_add_f32(dst + h * 32 + 3, v.w);
+                        }
+                    }
                 }
             }
         }
@@ -987,10 +1020,12 @@ template <bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     int W, int H, int C, const float* __restrict__ bg_color, const SplatRec* __restrict__ rec,
     const float* __restrict__ features, const float* __restrict__ final_Ts, const float* __restrict__ dL_dpixels,
-    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity) {
+    PoolView pool, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity,
+    const __grid_constant__ CUtensorMap dl_map, const int use_tma) {
     constexpr int CK = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint2 MetaS[kMetaCap];
+    __shared__ uint64_t dbar[kThreads / 32][2];  // per warp, per dL slab buffer: TMA completion
     __shared__ uint32_t Cdir[kMetaCap / kChunkEntries];
 
     const int tiles_x = (W + SGB_TILE - 1) / SGB_TILE;
@@ -1014,9 +1049,14 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     // ---- CTA prologue: directory + (id, mask) records of the tile list -> shared memory; background flag
     const uint32_t ncache = min(n, (uint32_t)kMetaCap);
     for (uint32_t k = tid; k * kChunkEntries < ncache; k += kThreads) Cdir[k] = chunk_of(pool, dbase, (int)k);
+    if (lane == 0) {
+        mbar_init(&dbar[warp][0], 1);
+        mbar_init(&dbar[warp][1], 1);
+        mbar_fence_init();
+    }
     int bg_nonzero = 0;
     for (int ch = tid; ch < C; ch += kThreads) bg_nonzero |= (bg_color[ch] != 0.f);
-    bg_nonzero = __syncthreads_or(bg_nonzero);   // also orders the Cdir stores
+    bg_nonzero = __syncthreads_or(bg_nonzero);   // also orders the Cdir stores and the barrier inits
     for (uint32_t e = tid; e < ncache; e += kThreads)
         MetaS[e] = __ldg(&pool.chunks[Cdir[e / kChunkEntries]].meta[e & (kChunkEntries - 1)]);
     __syncthreads();
@@ -1053,7 +1093,21 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
     const size_t d_stepslab = d_vec_ok ? CK * plane * sizeof(float) : 0;   // next slab
     const int d_bytes = d_vec_ok ? 16 : 0;
     const char* d_run = d_base;
+    // TMA path (image rows 16-byte aligned; the map is encoded per launch by the host): ONE instruction of one lane
+    // fetches the whole [16 ch][2 rows][16 px] box — rows below the image, columns right of it and channels >= C arrive
+    // as zeros — and none of it passes through the LSU data pipe (the four LDGSTS per lane it replaces were 64 of the
+    // ~210 L1 wavefronts per slab, and the L1 data pipe bounds this kernel).
+    uint32_t dphase = 0;  // bit b: parity the next wait on buffer b expects
     auto dissue = [&](int sl, int buf) {
+        if (use_tma) {
+            if (lane == 0) {
+                fence_proxy_async_smem();  // S of the previous segment was written to this memory by generic stores
+                mbar_arrive_expect_tx(&dbar[warp][buf], CK * 32 * sizeof(float));
+                tma_tile3d_g2s(&ws.DS[buf][0][0], &dl_map, (int)pix_min.x, (int)pix_min.y + 2 * warp, sl * CK,
+                               &dbar[warp][buf]);
+            }
+            return;
+        }
         if (rows16 && (sl + 1) * CK <= C) {
             float* dst = &ws.DS[buf][lane >> 3][d_pc * 4];
             const char* src = d_run;
@@ -1189,7 +1243,12 @@ __global__ void __launch_bounds__(kThreads, 2) chain_backward_warp_kernel(
         if (nslab > 1) fload(1);
         for (int sl = 0; sl < nslab; sl++) {
             const int buf = sl & 1;
-            cp_async_wait<0>();
+            if (use_tma) {
+                mbar_wait(&dbar[warp][buf], (dphase >> buf) & 1u);
+                dphase ^= 1u << buf;
+            } else {
+                cp_async_wait<0>();
+            }
             __syncwarp();  // DS[buf] landed, FT[buf] stored by every lane; DS/FT[buf ^ 1] are free
             if (sl + 1 < nslab) {
                 dissue(sl + 1, buf ^ 1);
@@ -1735,7 +1794,7 @@ int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t 
         return launch_dfeature_mma(ctx, in, dL_dpix, dL_dcolors, pv, s);  // opt-in experiment
     const int tiles = num_tiles(in);
     const int chunks = (in.C + 63) / 64;
-    const size_t smem_d = sizeof(float) * (64 * (SGB_TILE_PIX + 4) + 8 * 2 * 16 * 36);
+    const size_t smem_d = sizeof(float) * (64 * SGB_TILE_PIX + 8 * 2 * 16 * 36);
     static DeviceOnce attr_set;
     if (attr_set.first_use_on_device())
         SGB_CUDA(cudaFuncSetAttribute(dfeature_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
@@ -1744,6 +1803,34 @@ int blend_backward_v3_dfeature(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t 
     dfeature_gemm_kernel<64><<<tiles * chunks, kThreads, smem_d, s>>>(in.W, in.H, in.C, dL_dpix, pv, dL_dcolors);
     SGB_LAUNCH_CHECK("dfeature_gemm_kernel", in.debug, s);
     return SGB_OK;
+}
+
+// Tensor map of dL/dout (C, H, W) fp32 with a [16 ch][2 rows][16 px] box for the chain kernel's slab loads.  Returns
+// false (the kernel then stages the slabs with cp.async) when the layout does not meet the TMA rules (base and row
+// pitch multiples of 16 bytes) or the driver entry point is not available.  SGB_CHAIN_TMA=0 forces the cp.async path.
+static bool encode_dl_map(CUtensorMap* map, const float* dL_dpix, int W, int H, int C) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    memset(map, 0, sizeof(*map));
+    const char* off = getenv("SGB_CHAIN_TMA");
+    if (off && off[0] == '0') return false;
+    if (!encode || (W & 3) != 0 || (reinterpret_cast<uintptr_t>(dL_dpix) & 15) != 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+    const cuuint32_t box[3] = {SGB_TILE, 2, 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dL_dpix), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, GeomView g, BinView b, ImgView im,
@@ -1774,8 +1861,10 @@ int blend_backward_v3_chain(sgb_ctx* ctx, const sgb_view_inputs& in, int64_t R, 
         if (vec) chain_backward_gemm_kernel<true><<<tiles, kThreads, smem_g, s>>>(SGB_CHAIN_ARGS);
         else chain_backward_gemm_kernel<false><<<tiles, kThreads, smem_g, s>>>(SGB_CHAIN_ARGS);
     } else {
-        if (vec) chain_backward_warp_kernel<true><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS);
-        else chain_backward_warp_kernel<false><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS);
+        CUtensorMap dl_map;
+        const int use_tma = encode_dl_map(&dl_map, dL_dpix, in.W, in.H, in.C) ? 1 : 0;
+        if (vec) chain_backward_warp_kernel<true><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS, dl_map, use_tma);
+        else chain_backward_warp_kernel<false><<<tiles, kThreads, smem_w, s>>>(SGB_CHAIN_ARGS, dl_map, use_tma);
     }
 #undef SGB_CHAIN_ARGS
     SGB_LAUNCH_CHECK("chain backward kernel", in.debug, s);

@@ -13,8 +13,8 @@ __global__ void probe(const int* __restrict__ lane_off, int iters, long long* cy
     for (int i = threadIdx.x; i < 8192; i += blockDim.x) sm[i] = (float)i;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // each warp works in its own 4 KB window so that warps do not share lines
-    uint32_t base = (uint32_t)__cvta_generic_to_shared(sm) + (warp & 7) * 4096 + lane_off[lane];
+    // two 16 KB windows; every pattern stays below 12 KB
+    uint32_t base = (uint32_t)__cvta_generic_to_shared(sm) + (warp & 1) * 16384 + lane_off[lane];
     uint32_t acc = 0;
     __syncthreads();
     const long long t0 = clock64();
@@ -73,6 +73,14 @@ static int p_b1(int l) { return ((l >> 1) & 3) * 16; }                        //
 static int p_b21_4(int l) { return (((l >> 1) & 3) | ((l >> 4) << 2)) * 16; } // bits {4,2,1}: 8 chunks
 static int p_b0_3(int l) { return ((l & 1) | (((l >> 3) & 3) << 1)) * 16; }   // bits {4,3,0}: 8 chunks, 2 per quarter
 static int p_b20(int l) { return (l & 1) * 16 + ((l >> 2) & 1) * 32; }        // bits {2,0}
+static int g8(int l) { return (l & 1) | (((l >> 2) & 3) << 1); }
+static int g4(int l) { return ((l >> 1) & 1) | ((l >> 4) << 1); }
+static int p_g8_contig(int l) { return g8(l) * 16; }
+static int p_g4_32(int l) { return g4(l) * 32; }
+static int p_g8_1040(int l) { return g8(l) * 1040; }
+static int p_g8_144(int l) { return g8(l) * 144; }
+static int p_g4_144(int l) { return g4(l) * 144; }
+static int p_g8_272(int l) { return g8(l) * 272; }
 static int p_pairs16(int l) { return ((l & 7) * 2 + ((l >> 3) & 1)) * 16; }  // 16 distinct chunks, quarters 0/2 and 1/3 equal
 
 int main(int argc, char** argv) {
@@ -85,6 +93,9 @@ int main(int argc, char** argv) {
         {"v4 8 rows stride 144 B x 4 chunks distinct", 16, p_rows144_q}, {"v4 16 chunks, quarter pairs equal", 16, p_pairs16},
         {"v4 bits{4,1,0}", 16, p_and3_hi}, {"v4 bits{3,2}", 16, p_b32}, {"v4 bits{2,1}", 16, p_b1},
         {"v4 bits{4,2,1}", 16, p_b21_4}, {"v4 bits{4,3,0}", 16, p_b0_3}, {"v4 bits{2,0}", 16, p_b20},
+        {"v4 group8 contiguous (chain F)", 16, p_g8_contig}, {"v4 group4 x 32 B (chain D)", 16, p_g4_32},
+        {"v4 group8 rows stride 1040 B (dfeature d)", 16, p_g8_1040}, {"v4 group8 rows stride 144 B", 16, p_g8_144},
+        {"v4 group4 rows stride 144 B (dfeature w)", 16, p_g4_144}, {"v4 group8 rows stride 272 B", 16, p_g8_272},
         {"v2 all distinct (256 B)", 8, p_distinct8}, {"v2 lane&15", 8, p_and15_8}, {"v2 lane&7", 8, p_and7_8},
         {"v2 lane>>2", 8, p_shr2_8}, {"v2 lane>>3", 8, p_shr3_8},
         {"b32 all distinct", 4, p_distinct4}, {"b32 lane&7", 4, p_and7_4}, {"b32 lane>>3", 4, p_shr3_4},
