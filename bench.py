@@ -89,6 +89,24 @@ def build_info():
     return {"library": baked, "source_sha256_16": src, "lib_sha256_16": h, "matches_sources": baked.endswith(src)}
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1 on some
+# boxes), so main() points fd 1 at stderr for the whole run and the result goes to a private duplicate of the real stdout.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def traffic_for(kernel, src_hash):
     """Measured DRAM bytes per launch (ncu --set full), only when the capture was taken from THIS source tree."""
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -334,7 +352,7 @@ def run_cpu_reference(args, rank, world):
         "e2e": {"value": value, "unit": "Mviews/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------ roofline helpers
@@ -765,7 +783,7 @@ def run_k3(args, rank, world, local_rank):
             line["cpu_preprocess_torch"] = cpu_torch_preprocess_leg(P)
         except Exception as ex:  # pragma: no cover
             line["cpu_preprocess_torch"] = {"error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     h.finish()
 
 
@@ -903,7 +921,7 @@ def run_k2(args, rank, world, local_rank):
                                     "sample": f"full preprocess + 3 bands of 16 rows fwd, scaled; {smp['seconds_sample']:.1f} s"}
         except Exception as ex:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     h.finish()
 
 
@@ -1052,7 +1070,7 @@ def run_k4(args, rank, world, local_rank):
         "gpu_launches": launches[0], "cub_calls": launches[1], "clocks": clocks, "build": binfo,
         "per_rank_ms_per_step": rank_ms,
     })
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     h.finish()
 
 
@@ -1190,7 +1208,7 @@ def run_k5(args, rank, world, local_rank):
                                                               f"torch-CPU gather/accumulate {smp['accumulate_s']:.2f} s/view"}
         except Exception as ex:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     h.finish()
 
 
@@ -1204,6 +1222,7 @@ def main():
     ap.add_argument("--no-baselines", action="store_true", help="skip the reference-CUDA and CPU legs")
     ap.add_argument("--quick", action="store_true", help="skip the per-view cost spread")
     args = ap.parse_args()
+    claim_stdout()
     if args.steps is None:
         args.steps = {"K2": 40, "K3": 20, "K4": 3, "K5": 3}[args.config] if args.impl == "ours" else 2
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
